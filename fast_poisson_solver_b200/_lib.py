@@ -1,0 +1,86 @@
+"""ctypes binding of libfps_sm100.so (C ABI declared in include/fps_sm100.h).
+
+The library is built in-tree by ``fast_poisson_solver_b200.build`` (nvcc, sm_100a).  There is no
+Python/CPU fallback: if the shared object is missing, ``load()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfps_sm100.so")
+
+F = 700
+FP = 704
+K0 = 400
+NFREQ = 200
+NHIDDEN = 5
+ENGINE_SIMT = 0
+ENGINE_TCGEN05 = 1
+
+_f32p = C.POINTER(C.c_float)
+
+
+class FpsWeights(C.Structure):
+    _fields_ = [
+        ("h_freqs", _f32p),
+        ("h_coefficients", _f32p),
+        ("h_biases", _f32p),
+        ("h_w0", _f32p),
+        ("h_b0", _f32p),
+        ("h_wh", _f32p * NHIDDEN),
+        ("h_bh", _f32p * NHIDDEN),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/fps_sm100.h declares
+_vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
+SIGNATURES = {
+    "fps_last_error": (C.c_char_p, []),
+    "fps_version": (_i32, []),
+    "fps_create": (_i32, [C.POINTER(_vp), _i32, C.POINTER(FpsWeights), _i32, _i32]),
+    "fps_destroy": (_i32, [_vp]),
+    "fps_set_engine": (_i32, [_vp, _i32]),
+    "fps_get_engine": (_i32, [_vp]),
+    "fps_workspace_bytes": (C.c_size_t, [_vp]),
+    "fps_features": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "fps_gram_accum": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fps_colsum_accum": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fps_assemble_factor": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(_f64), C.POINTER(_f64), _i32, _vp, _vp, _vp]),
+    "fps_project_rhs": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "fps_solve_factored": (_i32, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "fps_reconstruct": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "fps_mse": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+class FpsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FpsError(
+            f"{LIB_PATH} is missing - build it with `python -m fast_poisson_solver_b200.build`. "
+            "This package has no CPU or pure-PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().fps_last_error()
+        raise FpsError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

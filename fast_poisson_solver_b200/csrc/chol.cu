@@ -1,0 +1,320 @@
+// Normal-equation assembly, blocked FP64 Cholesky and batched triangular solves on the 704x704
+// feature-dimension system.
+//
+// Reference: precompute_LHS_RHS (solver.py:187-199) builds, per lambda,
+//     LHS = lambda/N * DH^T DH + 1/N_bc * H_bc^T (I - 11^T/N_bc) H_bc
+// with a dense N_bc x N_bc centering matrix; solve() then calls torch.linalg.solve (LU) per
+// right-hand side (solver.py:305) and computes bias = -(1^T H_bc w - sum(bc)) / N_bc (:306).
+// Here the centering matrix is folded in as the rank-1 correction  Gbc - s s^T / N_bc  with
+// s = H_bc^T 1, the matrix is factored ONCE (it is symmetric positive semi-definite by
+// construction) and every solve is two triangular sweeps over all right-hand sides at once.
+//
+// Conditioning: cond(LHS) ~ 1e15 in fp64 and the matrix is exactly singular when
+// N + N_bc < 700 (the reference's own test fixture, grid_num=5).  fps_assemble_factor therefore
+// takes a diagonal shift `jitter` (absolute) chosen by the host: it starts at 0 and is raised only
+// when the factorisation reports a pivot <= eps*max_diag through `info`.
+#include "fps_common.cuh"
+#include <float.h>
+
+namespace fps {
+
+constexpr int CN = FP;   // matrix order incl. padding
+constexpr int CB = 32;   // panel width
+constexpr int CNB = CN / CB;  // 22 panels
+
+// ---- assemble ----------------------------------------------------------------------------------
+__global__ void assemble_kernel(const double* __restrict__ G, const double* __restrict__ Gbc,
+                                const double* __restrict__ s, double lam_over_n, double inv_nbc, double jitter,
+                                double* __restrict__ L) {
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < CN; j += blockDim.x) {
+    double v;
+    if (i < F && j < F) {
+      v = lam_over_n * G[(size_t)i * CN + j] + (Gbc[(size_t)i * CN + j] - s[i] * s[j] * inv_nbc) * inv_nbc;
+      if (i == j) v += jitter;
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    L[(size_t)i * CN + j] = v;
+  }
+}
+
+// max diagonal of the assembled matrix (first F entries) -> scal[0]; resets info.
+__global__ void diagmax_kernel(const double* __restrict__ L, double* __restrict__ scal, int* __restrict__ info) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) m = fmax(m, L[(size_t)i * CN + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)blockDim.x / 32; ++w) m = fmax(m, red[w]);
+    scal[0] = m;
+    *info = 0;
+  }
+}
+
+// ---- panel: factor the 32x32 diagonal block (every CTA, redundantly) and solve the rows below ----
+// L21 = A21 * L11^-T.  The factored diagonal block goes to Dfac (CTA 0 only) so that CTAs that are
+// still reading the unfactored block from L never race with the write-back; fixup_kernel installs
+// the diagonal blocks at the end.
+__global__ void __launch_bounds__(256)
+chol_panel_kernel(double* __restrict__ L, int kb, double* __restrict__ Dfac, const double* __restrict__ scal,
+                  int* __restrict__ info) {
+  __shared__ double D[CB][CB + 1];
+  const int k0 = kb * CB;
+  const int t = threadIdx.x;
+  for (int e = t; e < CB * CB; e += 256) D[e / CB][e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
+  const double tol = DBL_EPSILON * scal[0];
+  const double safe = scal[0] > 0.0 ? scal[0] : 1.0;
+  for (int j = 0; j < CB; ++j) {
+    __syncthreads();
+    double d = D[j][j];
+    const bool bad = !(d > tol);
+    if (bad) d = safe;  // keep the arithmetic finite; the host sees info != 0 and retries with a shift
+    const double ljj = sqrt(d);
+    __syncthreads();
+    if (t < CB) {
+      if (t == j) {
+        D[j][j] = ljj;
+        if (bad && blockIdx.x == 0) atomicCAS(info, 0, k0 + j + 1);
+      } else if (t > j) {
+        D[t][j] = D[t][j] / ljj;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = t + 256 * q;
+      const int i = e / CB, m = e % CB;
+      if (m > j && i >= m) D[i][m] -= D[i][j] * D[m][j];
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int e = t; e < CB * CB; e += 256) Dfac[(size_t)kb * CB * CB + e] = (e % CB <= e / CB) ? D[e / CB][e % CB] : 0.0;
+
+  const int r = k0 + CB + blockIdx.x * 256 + t;
+  if (r < CN) {
+    double x[CB];
+    double* row = L + (size_t)r * CN + k0;
+#pragma unroll
+    for (int j = 0; j < CB; ++j) x[j] = row[j];
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+      double sacc = x[j];
+#pragma unroll
+      for (int m = 0; m < j; ++m) sacc = fma(-x[m], D[j][m], sacc);
+      x[j] = sacc / D[j][j];
+    }
+#pragma unroll
+    for (int j = 0; j < CB; ++j) row[j] = x[j];
+  }
+}
+
+// ---- trailing update: A22 -= L21 L21^T on lower-triangular 64x64 tiles -----------------------------
+__global__ void __launch_bounds__(256)
+chol_update_kernel(double* __restrict__ L, int kb) {
+  __shared__ double Pi[64][CB + 1];
+  __shared__ double Pj[64][CB + 1];
+  const int base = (kb + 1) * CB;
+  int tile = blockIdx.x, ti, tj;
+  ti = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+  while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+  while (ti * (ti + 1) / 2 > tile) --ti;
+  tj = tile - ti * (ti + 1) / 2;
+  const int i0 = base + ti * 64, j0 = base + tj * 64;
+  const int k0 = kb * CB;
+  for (int e = threadIdx.x; e < 64 * CB; e += 256) {
+    const int r = e / CB, c = e % CB;
+    Pi[r][c] = (i0 + r < CN) ? L[(size_t)(i0 + r) * CN + k0 + c] : 0.0;
+    Pj[r][c] = (j0 + r < CN) ? L[(size_t)(j0 + r) * CN + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < CB; ++k) {
+    double pa[4], pb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) pa[a] = Pi[ty + 16 * a][k];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) pb[b] = Pj[tx + 16 * b][k];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(pa[a], pb[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+      if (i < CN && j <= i) L[(size_t)i * CN + j] -= acc[a][b];
+    }
+}
+
+// ---- fixup: install factored diagonal blocks, mirror L into the upper triangle (so that both
+// triangular sweeps read rows contiguously) --------------------------------------------------------
+__global__ void chol_fixup_kernel(double* __restrict__ L, const double* __restrict__ Dfac) {
+  const int i = blockIdx.x;
+  const int kb = i / CB;
+  for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+    double v;
+    if (j >= kb * CB) v = Dfac[(size_t)kb * CB * CB + (i - kb * CB) * CB + (j - kb * CB)];
+    else v = L[(size_t)i * CN + j];
+    L[(size_t)i * CN + j] = v;
+    if (j < i) L[(size_t)j * CN + i] = v;
+  }
+}
+
+int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
+                           int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,
+                           cudaStream_t st) {
+  FPS_REQUIRE(n_total > 0 && nbc_total > 0, "assemble: empty problem (N=%lld, N_bc=%lld)", (long long)n_total,
+              (long long)nbc_total);
+  // scratch in the partial workspace: [0] = max diag, then the 22 factored diagonal blocks
+  double* scal = ctx->partial;
+  double* Dfac = ctx->partial + 8;
+  for (int li = 0; li < n_lambda; ++li) {
+    double* Ll = L + (size_t)li * CN * CN;
+    const double lam = h_lambdas[li];
+    const double jitter = h_jitter ? h_jitter[li] : 0.0;
+    assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam / (double)n_total, 1.0 / (double)nbc_total, jitter, Ll);
+    diagmax_kernel<<<1, 256, 0, st>>>(Ll, scal, info + li);
+    for (int kb = 0; kb < CNB; ++kb) {
+      const int below = CN - (kb + 1) * CB;
+      const int pc = below > 0 ? (below + 255) / 256 : 1;
+      chol_panel_kernel<<<pc, 256, 0, st>>>(Ll, kb, Dfac, scal, info + li);
+      if (below > 0) {
+        const int t64 = (below + 63) / 64;
+        chol_update_kernel<<<t64 * (t64 + 1) / 2, 256, 0, st>>>(Ll, kb);
+      }
+    }
+    chol_fixup_kernel<<<CN, 256, 0, st>>>(Ll, Dfac);
+  }
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- batched solve  W = (L L^T)^-1 (scale R),  bias = -(s^T W - sum_bc)/N_bc ----------------------
+// One CTA owns SC right-hand-side columns and runs both sweeps entirely in shared memory; L (full,
+// mirrored) is streamed from L2.  Warp c solves the 32x32 diagonal systems of column c with lane = row.
+constexpr int SC = 8;
+
+__global__ void __launch_bounds__(256)
+solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R, int64_t ldr, int B, double scale,
+                      const double* __restrict__ s, const double* __restrict__ sum_bc, double inv_nbc,
+                      double* __restrict__ W, double* __restrict__ bias) {
+  extern __shared__ double sm[];
+  double* X = sm;                  // [CN][SC]
+  double* D = sm + CN * SC;        // [CB][CB+1] diagonal block
+  double* xb = D + CB * (CB + 1);  // [CB][SC] solved block
+  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
+  const int c0 = blockIdx.x * SC;
+  for (int e = t; e < CN * SC; e += 256) {
+    const int r = e / SC, c = e % SC;
+    X[e] = (c0 + c < B) ? scale * R[(int64_t)r * ldr + c0 + c] : 0.0;
+  }
+  // forward: L y = b
+  for (int kb = 0; kb < CNB; ++kb) {
+    const int k0 = kb * CB;
+    __syncthreads();
+    for (int e = t; e < CB * CB; e += 256) D[(e / CB) * (CB + 1) + e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
+    __syncthreads();
+    {
+      double x = X[(k0 + lane) * SC + warp];
+#pragma unroll 4
+      for (int j = 0; j < CB; ++j) {
+        double xj = __shfl_sync(0xffffffffu, x, j) / D[j * (CB + 1) + j];
+        if (lane == j) x = xj;
+        else if (lane > j) x = fma(-D[lane * (CB + 1) + j], xj, x);
+      }
+      X[(k0 + lane) * SC + warp] = x;
+      xb[lane * SC + warp] = x;
+    }
+    __syncthreads();
+    // rows below: X[r] -= sum_m L[r][k0+m] xb[m]  (read through the mirrored upper triangle: coalesced)
+    for (int r = k0 + CB + t; r < CN; r += 256) {
+      double acc[SC];
+#pragma unroll
+      for (int c = 0; c < SC; ++c) acc[c] = X[r * SC + c];
+#pragma unroll 4
+      for (int m = 0; m < CB; ++m) {
+        const double l = L[(size_t)(k0 + m) * CN + r];
+#pragma unroll
+        for (int c = 0; c < SC; ++c) acc[c] = fma(-l, xb[m * SC + c], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < SC; ++c) X[r * SC + c] = acc[c];
+    }
+  }
+  // backward: L^T w = y
+  for (int kb = CNB - 1; kb >= 0; --kb) {
+    const int k0 = kb * CB;
+    __syncthreads();
+    for (int e = t; e < CB * CB; e += 256) D[(e / CB) * (CB + 1) + e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
+    __syncthreads();
+    {
+      double x = X[(k0 + lane) * SC + warp];
+#pragma unroll 4
+      for (int j = CB - 1; j >= 0; --j) {
+        double xj = __shfl_sync(0xffffffffu, x, j) / D[j * (CB + 1) + j];
+        if (lane == j) x = xj;
+        else if (lane < j) x = fma(-D[j * (CB + 1) + lane], xj, x);  // (L^T)[lane][j] = L[j][lane]
+      }
+      X[(k0 + lane) * SC + warp] = x;
+      xb[lane * SC + warp] = x;
+    }
+    __syncthreads();
+    // rows above: X[r] -= sum_m L[k0+m][r] xb[m]
+    for (int r = t; r < k0; r += 256) {
+      double acc[SC];
+#pragma unroll
+      for (int c = 0; c < SC; ++c) acc[c] = X[r * SC + c];
+#pragma unroll 4
+      for (int m = 0; m < CB; ++m) {
+        const double l = L[(size_t)(k0 + m) * CN + r];
+#pragma unroll
+        for (int c = 0; c < SC; ++c) acc[c] = fma(-l, xb[m * SC + c], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < SC; ++c) X[r * SC + c] = acc[c];
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < CN * SC; e += 256) {
+    const int r = e / SC, c = e % SC;
+    if (c0 + c < B) W[(int64_t)r * ldr + c0 + c] = X[e];
+  }
+  // bias (solver.py:306): warp c reduces s^T w over the F real features
+  if (c0 + warp < B) {
+    double acc = 0.0;
+    for (int r = lane; r < F; r += 32) acc = fma(s[r], X[r * SC + warp], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) bias[c0 + warp] = -(acc - sum_bc[c0 + warp]) * inv_nbc;
+  }
+}
+
+int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
+                          const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st) {
+  if (B <= 0) return 0;
+  const size_t smem = (size_t)(CN * SC + CB * (CB + 1) + CB * SC) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FPS_CUDA(cudaFuncSetAttribute(solve_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  solve_factored_kernel<<<(B + SC - 1) / SC, 256, smem, st>>>(L, R, ldr, B, scale, s, sum_bc, 1.0 / (double)nbc_total,
+                                                              W, bias);
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fps

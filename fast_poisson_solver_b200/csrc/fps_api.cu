@@ -1,0 +1,203 @@
+// C-ABI entry points of libfps_sm100.so (declared in include/fps_sm100.h).
+// Context management, weight packing and the per-chunk layer pipeline of fps_features.
+#include "fps_common.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+namespace fps {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// Pad a (rows x cols) torch weight[out][in] to (FP x Kp), split into TF32 hi/lo planes on the host.
+static int upload_layer(Layer& L, const float* w, const float* b, int cols, int Kp) {
+  std::vector<float> hi((size_t)FP * Kp, 0.f), lo((size_t)FP * Kp, 0.f), bias(FP, 0.f);
+  for (int r = 0; r < F; ++r) {
+    for (int c = 0; c < cols; ++c) {
+      const float v = w[(size_t)r * cols + c];
+      uint32_t u;
+      memcpy(&u, &v, 4);
+      u &= 0xffffe000u;
+      float h;
+      memcpy(&h, &u, 4);
+      hi[(size_t)r * Kp + c] = h;
+      lo[(size_t)r * Kp + c] = v - h;
+    }
+    bias[r] = b[r];
+  }
+  L.Kp = Kp;
+  const size_t bytes = (size_t)FP * Kp * sizeof(float);
+  FPS_CUDA(cudaMalloc(&L.w_hi, bytes));
+  FPS_CUDA(cudaMalloc(&L.w_lo, bytes));
+  FPS_CUDA(cudaMalloc(&L.bias, FP * sizeof(float)));
+  FPS_CUDA(cudaMemcpy(L.w_hi, hi.data(), bytes, cudaMemcpyHostToDevice));
+  FPS_CUDA(cudaMemcpy(L.w_lo, lo.data(), bytes, cudaMemcpyHostToDevice));
+  FPS_CUDA(cudaMemcpy(L.bias, bias.data(), FP * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace fps
+
+using namespace fps;
+
+extern "C" {
+
+const char* fps_last_error(void) { return g_err; }
+int fps_version(void) { return 100; }
+
+int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points, int engine) {
+  FPS_REQUIRE(out && w, "fps_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  FPS_REQUIRE(e == cudaSuccess && ndev > 0,
+              "fps_create: no CUDA device (%s). libfps_sm100 has no CPU fallback.", cudaGetErrorString(e));
+  FPS_REQUIRE(device >= 0 && device < ndev, "fps_create: device %d out of range (%d devices)", device, ndev);
+  FPS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FPS_CUDA(cudaGetDeviceProperties(&prop, device));
+  FPS_REQUIRE(prop.major == 10, "fps_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+              device, prop.major, prop.minor);
+  fps_ctx* ctx = new fps_ctx();
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  ctx->engine = engine;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 16384;
+  int rc = upload_layer(ctx->layer[0], w->h_w0, w->h_b0, K0, K0P);
+  for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer(ctx->layer[l + 1], w->h_wh[l], w->h_bh[l], F, FP);
+  if (rc) { fps_destroy(ctx); return rc; }
+  double ffm[4 * NFREQ];
+  for (int j = 0; j < NFREQ; ++j) {
+    ffm[j] = w->h_freqs[j];
+    ffm[NFREQ + j] = w->h_freqs[NFREQ + j];
+    ffm[2 * NFREQ + j] = w->h_coefficients[j];
+    ffm[3 * NFREQ + j] = w->h_biases[j];
+  }
+  FPS_CUDA(cudaMalloc(&ctx->ffm, sizeof(ffm)));
+  FPS_CUDA(cudaMemcpy(ctx->ffm, ffm, sizeof(ffm), cudaMemcpyHostToDevice));
+  const size_t plane = (size_t)ctx->chunk * NSTREAM * FP * sizeof(float);
+  for (int i = 0; i < 2; ++i) {
+    FPS_CUDA(cudaMalloc(&ctx->act[i].hi, plane));
+    FPS_CUDA(cudaMalloc(&ctx->act[i].lo, plane));
+  }
+  ctx->partial_bytes = (size_t)1024 * 64 * 64 * sizeof(double);  // 32 MiB of split-K tiles
+  FPS_CUDA(cudaMalloc(&ctx->partial, ctx->partial_bytes));
+  ctx->workspace_bytes = 4 * plane + ctx->partial_bytes;
+  if (tc_init(ctx)) { fps_destroy(ctx); return 3; }
+  *out = ctx;
+  return 0;
+}
+
+int fps_destroy(fps_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  tc_destroy(ctx);
+  for (int l = 0; l < NLAYER; ++l) {
+    cudaFree(ctx->layer[l].w_hi);
+    cudaFree(ctx->layer[l].w_lo);
+    cudaFree(ctx->layer[l].bias);
+  }
+  cudaFree(ctx->ffm);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->act[i].hi);
+    cudaFree(ctx->act[i].lo);
+  }
+  cudaFree(ctx->partial);
+  delete ctx;
+  return 0;
+}
+
+int fps_set_engine(fps_ctx* ctx, int engine) {
+  FPS_REQUIRE(ctx, "null ctx");
+  FPS_REQUIRE(engine == FPS_ENGINE_SIMT || engine == FPS_ENGINE_TCGEN05, "unknown engine %d", engine);
+  ctx->engine = engine;
+  return 0;
+}
+int fps_get_engine(const fps_ctx* ctx) { return ctx ? ctx->engine : -1; }
+size_t fps_workspace_bytes(const fps_ctx* ctx) { return ctx ? ctx->workspace_bytes : 0; }
+
+int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, float* H, float* DH, int64_t ld,
+                 void* stream) {
+  FPS_REQUIRE(ctx && x && y && H, "fps_features: null argument");
+  FPS_REQUIRE(ld >= FP && ld % 4 == 0, "fps_features: ld=%lld must be >= %d and a multiple of 4", (long long)ld, FP);
+  FPS_REQUIRE((uintptr_t)H % 16 == 0 && (uintptr_t)DH % 16 == 0, "fps_features: H/DH must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int streams = DH ? NSTREAM : 1;
+  // value-only evaluation carries one stream, so four times as many points fit a workspace wave
+  const int64_t wave = (int64_t)ctx->chunk * (NSTREAM / streams);
+  for (int64_t p0 = 0; p0 < n; p0 += wave) {
+    const int64_t np = (n - p0 < wave) ? n - p0 : wave;
+    int cur = 0;
+    if (int rc = launch_fourier(ctx, x + p0, y + p0, np, streams, ctx->act[cur], st)) return rc;
+    for (int l = 0; l < NLAYER; ++l) {
+      const bool last = (l == NLAYER - 1);
+      float* Hc = H + p0 * ld;
+      float* DHc = DH ? DH + p0 * ld : nullptr;
+      int rc;
+      if (ctx->engine == FPS_ENGINE_TCGEN05)
+        rc = launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, streams, last, Hc, DHc, ld, st);
+      else
+        rc = launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, streams, last, Hc, DHc, ld, st);
+      if (rc) return rc;
+      cur ^= 1;
+    }
+  }
+  return 0;
+}
+
+int fps_gram_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* G64, void* stream) {
+  FPS_REQUIRE(ctx && A && G64, "fps_gram_accum: null argument");
+  FPS_REQUIRE(ld >= FP, "fps_gram_accum: ld=%lld < %d", (long long)ld, FP);
+  return launch_atb_f64(ctx, A, ld, FP, A, ld, FP, n, G64, FP, true, (cudaStream_t)stream);
+}
+
+int fps_colsum_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* s64, void* stream) {
+  FPS_REQUIRE(ctx && A && s64, "fps_colsum_accum: null argument");
+  FPS_REQUIRE(ld >= FP, "fps_colsum_accum: ld=%lld < %d", (long long)ld, FP);
+  return launch_colsum(A, n, ld, s64, (cudaStream_t)stream);
+}
+
+int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, const double* s64, int64_t n_total,
+                        int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L64,
+                        int* info, void* stream) {
+  FPS_REQUIRE(ctx && G64 && Gbc64 && s64 && h_lambdas && L64 && info && n_lambda > 0, "fps_assemble_factor: bad argument");
+  return launch_assemble_factor(ctx, G64, Gbc64, s64, n_total, nbc_total, h_lambdas, h_jitter, n_lambda, L64, info,
+                                (cudaStream_t)stream);
+}
+
+int fps_project_rhs(fps_ctx* ctx, const float* DH, int64_t n, int64_t ld, const float* Fm, int64_t ldf, int B,
+                    double* R64, int64_t ldr, void* stream) {
+  FPS_REQUIRE(ctx && DH && Fm && R64, "fps_project_rhs: null argument");
+  FPS_REQUIRE(ld >= FP && ldf >= B && ldr >= B, "fps_project_rhs: bad leading dimension");
+  return launch_atb_f64(ctx, DH, ld, FP, Fm, ldf, B, n, R64, ldr, false, (cudaStream_t)stream);
+}
+
+int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64_t ldr, int B, double scale,
+                       const double* s64, const double* sum_bc64, int64_t nbc_total, double* W64, double* bias64,
+                       void* stream) {
+  FPS_REQUIRE(ctx && L64 && R64 && s64 && sum_bc64 && W64 && bias64, "fps_solve_factored: null argument");
+  FPS_REQUIRE(ldr >= B && nbc_total > 0, "fps_solve_factored: bad argument");
+  return launch_solve_factored(L64, R64, ldr, B, scale, s64, sum_bc64, nbc_total, W64, bias64, (cudaStream_t)stream);
+}
+
+int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
+                    const double* bias64, int B, float* out, int64_t ldo, void* stream) {
+  FPS_REQUIRE(ctx && A && W64 && out, "fps_reconstruct: null argument");
+  FPS_REQUIRE(ldw >= B && ldo >= B, "fps_reconstruct: bad leading dimension");
+  return launch_reconstruct(ctx, A, n, ld, W64, ldw, bias64, B, out, ldo, (cudaStream_t)stream);
+}
+
+int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream) {
+  FPS_REQUIRE(ctx && pred && ref && loss64 && n > 0, "fps_mse: bad argument");
+  return launch_mse(pred, ref, n, loss64, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared declarations for libfps_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/fps_sm100.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libfps_sm100 is written for sm_100a (B200) only"
+#endif
+
+namespace fps {
+
+constexpr int F = FPS_F;          // 700 features
+constexpr int FP = FPS_FP;        // padded feature dimension (row stride of every activation)
+constexpr int K0 = FPS_K0;        // 400 Fourier inputs
+constexpr int K0P = 416;          // K0 padded to a multiple of 32 (one 128-byte TMA/UMMA K-chunk)
+constexpr int NFREQ = FPS_NFREQ;  // 200
+constexpr int NLAYER = 1 + FPS_NHIDDEN;  // mapping.linear + 5 hidden
+constexpr int NSTREAM = 4;        // value, d/dx, d/dy, laplacian
+
+// Activation planes.  A layer input for P points is a (rows = P*S, K) row-major matrix, row index
+// r = point*S + stream (S = 4 for PDE points, 1 for boundary points), stored as two fp32 planes:
+//   hi = value with the low 13 mantissa bits cleared (exactly a TF32 number)
+//   lo = value - hi (exact in fp32; its top 11 bits are what the tensor core consumes)
+// so that hi + lo reproduces the fp32 activation exactly and A*B ~ Ahi*Bhi + Ahi*Blo + Alo*Bhi.
+struct ActPlanes {
+  float* hi;
+  float* lo;
+};
+
+struct Layer {
+  float* w_hi;   // (FP, Kp) row-major, K-major == torch weight[out][in], zero padded
+  float* w_lo;
+  float* bias;   // (FP) zero padded
+  int Kp;        // padded K (K0P for layer 0, FP otherwise)
+};
+
+}  // namespace fps
+
+struct fps_ctx {
+  int device;
+  int engine;
+  int chunk;              // points per wave
+  int sm_count;
+  fps::Layer layer[fps::NLAYER];
+  double* ffm;            // 4*NFREQ doubles: F0 | F1 | coefficients | biases
+  fps::ActPlanes act[2];  // ping-pong, each plane chunk*4*FP floats
+  double* partial;        // split-K partial tiles for the fp64 GEMMs
+  size_t partial_bytes;
+  size_t workspace_bytes;
+  void* tc_state;         // engine-private (tensor maps), owned by layer_tc.cu
+};
+
+namespace fps {
+
+void set_error(const char* fmt, ...);
+
+#define FPS_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      fps::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define FPS_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      fps::set_error(__VA_ARGS__);    \
+      return 2;                       \
+    }                                 \
+  } while (0)
+
+// ---- kernel launchers (one translation unit each) -------------------------------------------
+int launch_fourier(const fps_ctx* ctx, const double* x, const double* y, int64_t n, int streams,
+                   ActPlanes out, cudaStream_t st);
+
+// One dense layer + tanh-derivative epilogue for `points` points with `streams` streams.
+// last = write H (and DH when streams == 4) instead of the next layer's planes.
+int launch_layer_simt(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int64_t points, int streams,
+                      bool last, float* H, float* DH, int64_t ld, cudaStream_t st);
+int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int64_t points, int streams,
+                    bool last, float* H, float* DH, int64_t ld, cudaStream_t st);
+int tc_init(fps_ctx* ctx);
+void tc_destroy(fps_ctx* ctx);
+
+// C (M x Ncols, ldc) fp64 += A^T B over n rows; A (n, lda) fp32 M columns, B (n, ldb) fp32 Ncols columns.
+// symmetric: A == B, only tiles with j <= i are computed and mirrored.
+int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const float* B, int64_t ldb, int Ncols,
+                   int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st);
+int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st);
+int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
+                           int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,
+                           cudaStream_t st);
+int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
+                          const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st);
+int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
+                       const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
+int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st);
+
+// ---- small device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__device__ __forceinline__ void split_store(float* hi, float* lo, float v) {
+  float h = tf32_hi(v);
+  *hi = h;
+  *lo = v - h;
+}
+
+}  // namespace fps

@@ -1,0 +1,451 @@
+// FP64-accumulated contractions over fp32 feature matrices (DMMA m8n8k4 tensor path).
+//
+//   atb      C(M x Nc) += A^T B   over n rows      Gram  DH^T DH        solver.py:167
+//                                                  BC    H_bc^T H_bc    solver.py:196
+//                                                  RHS   DH^T F         solver.py:197 + :301
+//   nn       out(n x B) = A W + bias               u = H w + b, f = DH w, u_bc = H_bc w + b
+//                                                                        solver.py:327-330
+// Why fp64: the normal matrix has cond ~1e15; accumulating the Gram or the RHS
+// projection at fp32 grade moves u by 1e-4..3e-2, far beyond the 1e-5 parity bar.  Inputs stay
+// fp32 in HBM (that is what the feature kernel produces) and are widened on the way into shared
+// memory, so HBM traffic is the fp32 footprint.
+//
+// Split-K (over rows) partial tiles are written to a workspace and summed in a fixed order by a
+// second kernel, so results are bit-reproducible for a given (n, chunking) - no fp64 atomics.
+#include "fps_common.cuh"
+#include <algorithm>
+
+namespace fps {
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int GT = 64;         // output tile edge
+constexpr int GK = 32;         // rows (contraction) per step
+constexpr int GS = GT + 4;     // smem row stride in doubles: == 4 (mod 16) -> conflict-free fragment loads
+constexpr int GTHREADS = 128;  // 4 warps, each a 32x32 sub-tile
+
+// Load a (GK x GT) fp32 tile whose rows are contraction indices: element (r, c) = P[(k0+r)*ld + c0+c],
+// zero outside [kend) x [ncols).  16 floats per thread as 4 float4 (scalar fallback when unaligned).
+struct TileRegs {
+  float4 v[4];
+};
+
+__device__ __forceinline__ void load_tile_kn(TileRegs& R, const float* __restrict__ P, int64_t ld, int64_t k0,
+                                             int64_t kend, int c0, int ncols, bool vec_ok) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int idx = q * GTHREADS + threadIdx.x;
+    const int r = idx / 16, c = (idx % 16) * 4;
+    float4 v = make_float4(0, 0, 0, 0);
+    const int64_t k = k0 + r;
+    if (k < kend) {
+      const float* p = P + k * ld + c0 + c;
+      if (vec_ok && c0 + c + 3 < ncols) {
+        v = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        if (c0 + c + 0 < ncols) v.x = __ldg(p + 0);
+        if (c0 + c + 1 < ncols) v.y = __ldg(p + 1);
+        if (c0 + c + 2 < ncols) v.z = __ldg(p + 2);
+        if (c0 + c + 3 < ncols) v.w = __ldg(p + 3);
+      }
+    }
+    R.v[q] = v;
+  }
+}
+
+__device__ __forceinline__ void store_tile_kn(const TileRegs& R, double* S) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int idx = q * GTHREADS + threadIdx.x;
+    const int r = idx / 16, c = (idx % 16) * 4;
+    double2* d = reinterpret_cast<double2*>(S + r * GS + c);
+    d[0] = make_double2((double)R.v[q].x, (double)R.v[q].y);
+    d[1] = make_double2((double)R.v[q].z, (double)R.v[q].w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C_partial[slice][tile] = A^T B over this slice's rows
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GTHREADS)
+atb_f64_kernel(const float* __restrict__ A, int64_t lda, int M, const float* __restrict__ B, int64_t ldb, int Nc,
+               int64_t n, int64_t rows_per_slice, int tiles_j, int symmetric, double* __restrict__ partial,
+               int vecA, int vecB) {
+  __shared__ __align__(16) double As[GK * GS];
+  __shared__ __align__(16) double Bs[GK * GS];
+  int ti, tj;
+  if (symmetric) {  // blockIdx.x enumerates the lower triangle: ti >= tj
+    int t = blockIdx.x;
+    ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tj = t - ti * (ti + 1) / 2;
+  } else {
+    ti = blockIdx.x / tiles_j;
+    tj = blockIdx.x % tiles_j;
+  }
+  const int64_t kbeg = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t kend = min(n, kbeg + rows_per_slice);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int wi = warp / 2, wj = warp % 2;
+  const int lr = lane / 4, lc = lane % 4;
+
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+
+  TileRegs ra, rb;
+  load_tile_kn(ra, A, lda, kbeg, kend, ti * GT, M, vecA);
+  load_tile_kn(rb, B, ldb, kbeg, kend, tj * GT, Nc, vecB);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += GK) {
+    __syncthreads();
+    store_tile_kn(ra, As);
+    store_tile_kn(rb, Bs);
+    __syncthreads();
+    if (k0 + GK < kend) {
+      load_tile_kn(ra, A, lda, k0 + GK, kend, ti * GT, M, vecA);
+      load_tile_kn(rb, B, ldb, k0 + GK, kend, tj * GT, Nc, vecB);
+    }
+#pragma unroll
+    for (int kk = 0; kk < GK / 4; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + lc) * GS + wi * 32 + i * 8 + lr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[(kk * 4 + lc) * GS + wj * 32 + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma8x8x4(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+  double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (GT * GT);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = wi * 32 + i * 8 + lr, cc = wj * 32 + j * 8 + lc * 2;
+      *reinterpret_cast<double2*>(out + r * GT + cc) = make_double2(c[i][j][0], c[i][j][1]);
+    }
+}
+
+// C += sum_slices partial (fixed order), mirrored for symmetric products.
+__global__ void atb_reduce_kernel(const double* __restrict__ partial, int ntiles, int nslices, int tiles_j,
+                                  int symmetric, int M, int Nc, double* __restrict__ C, int64_t ldc) {
+  const int tile = blockIdx.x;
+  int ti, tj;
+  if (symmetric) {
+    ti = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+    while (ti * (ti + 1) / 2 > tile) --ti;
+    tj = tile - ti * (ti + 1) / 2;
+  } else {
+    ti = tile / tiles_j;
+    tj = tile % tiles_j;
+  }
+  for (int e = threadIdx.x; e < GT * GT; e += blockDim.x) {
+    double s = 0.0;
+    for (int sl = 0; sl < nslices; ++sl) s += partial[((size_t)sl * ntiles + tile) * (GT * GT) + e];
+    const int r = ti * GT + e / GT, c = tj * GT + e % GT;
+    if (r < M && c < Nc) {
+      if (!symmetric) {
+        C[(int64_t)r * ldc + c] += s;
+      } else if (c <= r) {
+        C[(int64_t)r * ldc + c] += s;
+        if (c < r) C[(int64_t)c * ldc + r] += s;
+      }
+    }
+  }
+}
+
+// Few right-hand sides (B <= 8): R(FP x B) += DH^T F is a streaming GEMV bounded by the HBM read of DH.
+// Each thread owns up to 3 feature columns (t, t+256, t+512) and B fp64 accumulators per column.
+template <int NB>
+__global__ void __launch_bounds__(256)
+atb_small_kernel(const float* __restrict__ A, int64_t lda, int M, const float* __restrict__ B, int64_t ldb,
+                 int nb, int64_t n, int64_t rows_per_cta, double* __restrict__ partial) {
+  const int t = threadIdx.x;
+  double acc[3][NB];
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[q][j] = 0.0;
+  const int64_t kbeg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t kend = min(n, kbeg + rows_per_cta);
+  const bool has2 = t + 512 < M;
+  for (int64_t k = kbeg; k < kend; k += 4) {
+    float a[4][3], f[4][NB];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = k + u < kend;
+      const float* row = A + (k + u) * lda;
+      a[u][0] = ok ? __ldg(row + t) : 0.f;
+      a[u][1] = ok ? __ldg(row + t + 256) : 0.f;
+      a[u][2] = (ok && has2) ? __ldg(row + t + 512) : 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) f[u][j] = (ok && j < nb) ? __ldg(B + (k + u) * ldb + j) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[q][j] = fma((double)a[u][q], (double)f[u][j], acc[q][j]);
+  }
+  double* out = partial + (size_t)blockIdx.x * (768 * NB);
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) out[(t + q * 256) * NB + j] = acc[q][j];
+}
+
+template <int NB>
+__global__ void atb_small_reduce_kernel(const double* __restrict__ partial, int nctas, int M, int B,
+                                        double* __restrict__ C, int64_t ldc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * NB) return;
+  const int r = e / NB, j = e % NB;
+  if (j >= B) return;
+  double s = 0.0;
+  for (int c = 0; c < nctas; ++c) s += partial[(size_t)c * (768 * NB) + e];
+  C[(int64_t)r * ldc + j] += s;
+}
+
+int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const float* B, int64_t ldb, int Nc,
+                   int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st) {
+  if (n <= 0 || M <= 0 || Nc <= 0) return 0;
+  FPS_REQUIRE(M <= FP, "atb: M=%d exceeds %d", M, FP);
+  if (!symmetric && Nc <= 8) {
+    int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 4, (n + 63) / 64);
+    ctas = std::min<int64_t>(ctas, (int64_t)(ctx->partial_bytes / (768 * 8 * sizeof(double))));
+    const int64_t rpc = ((n + ctas - 1) / ctas + 3) / 4 * 4;
+    ctas = (n + rpc - 1) / rpc;
+    // columns t+256 always < 704 <= lda; t+512 guarded by has2
+    FPS_REQUIRE(M > 512 && lda >= M, "atb small path expects the padded feature matrix");
+#define FPS_SMALL(NB_)                                                                                        \
+  atb_small_kernel<NB_><<<(unsigned)ctas, 256, 0, st>>>(A, lda, M, B, ldb, Nc, n, rpc, ctx->partial);            \
+  atb_small_reduce_kernel<NB_><<<(M * NB_ + 255) / 256, 256, 0, st>>>(ctx->partial, (int)ctas, M, Nc, C, ldc)
+    if (Nc == 1) { FPS_SMALL(1); }
+    else if (Nc == 2) { FPS_SMALL(2); }
+    else if (Nc <= 4) { FPS_SMALL(4); }
+    else { FPS_SMALL(8); }
+#undef FPS_SMALL
+    FPS_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const int tiles_i = (M + GT - 1) / GT, tiles_j = (Nc + GT - 1) / GT;
+  const int ntiles = symmetric ? tiles_i * (tiles_i + 1) / 2 : tiles_i * tiles_j;
+  const size_t tile_bytes = (size_t)GT * GT * sizeof(double);
+  const int64_t max_ctas = (int64_t)(ctx->partial_bytes / tile_bytes);
+  FPS_REQUIRE(ntiles <= max_ctas, "atb: %d tiles exceed the partial workspace", ntiles);
+  int64_t slices = ((int64_t)ctx->sm_count * 4 + ntiles - 1) / ntiles;
+  slices = std::min<int64_t>(slices, (n + 4 * GK - 1) / (4 * GK));
+  slices = std::min<int64_t>(slices, max_ctas / ntiles);
+  slices = std::max<int64_t>(slices, 1);
+  const int64_t rps = ((n + slices - 1) / slices + GK - 1) / GK * GK;
+  slices = (n + rps - 1) / rps;
+  const int vecA = (lda % 4 == 0) && ((uintptr_t)A % 16 == 0);
+  const int vecB = (ldb % 4 == 0) && ((uintptr_t)B % 16 == 0);
+  dim3 grid((unsigned)ntiles, (unsigned)slices);
+  atb_f64_kernel<<<grid, GTHREADS, 0, st>>>(A, lda, M, B, ldb, Nc, n, rps, tiles_j, symmetric ? 1 : 0, ctx->partial,
+                                            vecA, vecB);
+  FPS_CUDA(cudaGetLastError());
+  atb_reduce_kernel<<<ntiles, 256, 0, st>>>(ctx->partial, ntiles, (int)slices, tiles_j, symmetric ? 1 : 0, M, Nc, C,
+                                            ldc);
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums in fp64 (H_bc^T 1, solver.py:176-178).  N_bc is small (4G+4); one CTA per 64 columns.
+// ------------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const float* __restrict__ A, int64_t n, int64_t ld, double* __restrict__ s64) {
+  __shared__ double red[4][64];
+  const int c = blockIdx.x * 64 + threadIdx.x % 64;
+  const int g = threadIdx.x / 64;
+  double s = 0.0;
+  for (int64_t r = g; r < n; r += 4) s += (double)A[r * ld + c];
+  red[g][threadIdx.x % 64] = s;
+  __syncthreads();
+  if (g == 0) s64[c] += red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st) {
+  if (n <= 0) return 0;
+  colsum_kernel<<<FP / 64, 256, 0, st>>>(A, n, ld, s64);
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out(n x B) = A(n x FP) W(FP x B) + bias, fp64 accumulation, fp32 in / fp32 out.
+// Tile 64 rows x 64 columns, K steps of 32; A fragment loads want a row stride == 4 (mod 16).
+// ------------------------------------------------------------------------------------------------
+constexpr int NS_A = GK + 4;  // 36
+
+__global__ void __launch_bounds__(GTHREADS)
+nn_f64_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
+              const double* __restrict__ bias, int B, float* __restrict__ out, int64_t ldo) {
+  __shared__ __align__(16) double As[GT * NS_A];
+  __shared__ __align__(16) double Ws[GK * GS];
+  const int64_t r0 = (int64_t)blockIdx.x * GT;
+  const int c0 = blockIdx.y * GT;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int wi = warp / 2, wj = warp % 2;
+  const int lr = lane / 4, lc = lane % 4;
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+
+  for (int k0 = 0; k0 < FP; k0 += GK) {
+    __syncthreads();
+    // A tile: 64 rows x 32 k, 512 float4, 4 per thread
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * GTHREADS + threadIdx.x;
+      const int r = idx / 8, kq = (idx % 8) * 4;
+      float4 v = make_float4(0, 0, 0, 0);
+      if (r0 + r < n) v = __ldg(reinterpret_cast<const float4*>(A + (r0 + r) * ld + k0 + kq));
+      double2* d = reinterpret_cast<double2*>(As + r * NS_A + kq);
+      d[0] = make_double2((double)v.x, (double)v.y);
+      d[1] = make_double2((double)v.z, (double)v.w);
+    }
+    // W tile: 32 k x 64 columns of doubles, 2048 doubles, 16 per thread
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = q * GTHREADS + threadIdx.x;
+      const int r = idx / GT, cc = idx % GT;
+      Ws[r * GS + cc] = (c0 + cc < B) ? W[(int64_t)(k0 + r) * ldw + c0 + cc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK / 4; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[(wi * 32 + i * 8 + lr) * NS_A + kk * 4 + lc];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[(kk * 4 + lc) * GS + wj * 32 + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma8x8x4(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = r0 + wi * 32 + i * 8 + lr;
+      const int cc = c0 + wj * 32 + j * 8 + lc * 2;
+      if (r < n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (cc + e < B) out[r * ldo + cc + e] = (float)(c[i][j][e] + (bias ? bias[cc + e] : 0.0));
+      }
+    }
+}
+
+// Few right-hand sides: one warp per row, W columns staged in shared memory; HBM-bound on A.
+template <int NB>
+__global__ void __launch_bounds__(256)
+nn_small_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
+                const double* __restrict__ bias, int B, float* __restrict__ out, int64_t ldo) {
+  __shared__ double Ws[FP * NB];
+  for (int e = threadIdx.x; e < FP * NB; e += blockDim.x) {
+    const int k = e / NB, j = e % NB;
+    Ws[e] = (j < B) ? W[(int64_t)k * ldw + j] : 0.0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < n; r += nwarps) {
+    const float4* row = reinterpret_cast<const float4*>(A + r * ld);
+    double acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = 0.0;
+    float4 v[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {  // 176 float4 per row: 5 full rounds of 32 lanes + 16
+      const int i4 = q * 32 + lane;
+      v[q] = (i4 < FP / 4) ? __ldg(row + i4) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const int i4 = q * 32 + lane;
+      if (i4 < FP / 4) {
+        const double* w = Ws + (size_t)i4 * 4 * NB;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          acc[j] = fma((double)v[q].x, w[0 * NB + j], acc[j]);
+          acc[j] = fma((double)v[q].y, w[1 * NB + j], acc[j]);
+          acc[j] = fma((double)v[q].z, w[2 * NB + j], acc[j]);
+          acc[j] = fma((double)v[q].w, w[3 * NB + j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (j < B) out[r * ldo + j] = (float)(acc[j] + (bias ? bias[j] : 0.0));
+    }
+  }
+}
+
+int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
+                       const double* bias, int B, float* out, int64_t ldo, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  FPS_REQUIRE(ld % 4 == 0 && (uintptr_t)A % 16 == 0 && ld >= FP, "reconstruct: A must be 16-byte aligned, ld %% 4 == 0, ld >= %d", FP);
+  if (B <= 4) {
+    const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
+    if (B == 1) nn_small_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    else if (B == 2) nn_small_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    else nn_small_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+  } else {
+    dim3 grid((unsigned)((n + GT - 1) / GT), (unsigned)((B + GT - 1) / GT));
+    nn_f64_kernel<<<grid, GTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+  }
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// mean((pred - ref)^2) in fp64, single CTA (used only by the multi-lambda sweep, solver.py:312-314).
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ ref, int64_t n,
+                           double* __restrict__ loss) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)pred[i] - (double)ref[i];
+    s = fma(d, d, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) loss[0] = s / (double)n;
+  }
+}
+
+int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st) {
+  mse_kernel<<<1, 1024, 0, st>>>(pred, ref, n, loss);
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fps

@@ -1,0 +1,119 @@
+/* fps_sm100.h  --  C ABI of libfps_sm100.so, the B200 (sm_100a) implementation of the
+ * fast-poisson-solver hot path:  Solver.precompute(x_pde, y_pde, x_bc, y_bc) + Solver.solve(f, bc).
+ *
+ * The reference (matthiasnwt/fast-poisson-solver) is pure Python and has no FFI; every entry point
+ * below replaces a span of reference Python that a maintainer would swap for a ctypes call
+ * (see INTEGRATION.md for the binding).  Citations are file:line in the reference checkout,
+ * relative to fast_poisson_solver/.
+ *
+ * Conventions
+ *   - every data pointer is a caller-owned DEVICE pointer unless its name starts with "h_";
+ *   - matrices are row-major with an explicit leading dimension in elements;
+ *   - FPS_F = 700 features, padded to FPS_FP = 704 in every feature-dimension buffer; the pad
+ *     columns of H / DH / H_bc are written as zero by the library;
+ *   - stream is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless stated;
+ *   - return value 0 = ok, non-zero = error; fps_last_error() gives the message (per thread);
+ *   - one host thread per context; a context owns its packed weights and a point-chunk workspace,
+ *     nothing else is allocated by the library.
+ */
+#ifndef FPS_SM100_H
+#define FPS_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPS_F 700        /* width of the feature network, resources/infos.yaml:859           */
+#define FPS_FP 704       /* FPS_F padded to a multiple of 64                                  */
+#define FPS_K0 400       /* 2 * ffm.num Fourier inputs, resources/infos.yaml:843-848          */
+#define FPS_NFREQ 200
+#define FPS_NHIDDEN 5    /* depth-1 Linear(700,700)+Tanh blocks, model.py:49-60               */
+
+#define FPS_ENGINE_SIMT 0     /* fp32 FFMA layer kernel (bring-up / cross-check engine)        */
+#define FPS_ENGINE_TCGEN05 1  /* 3xTF32 tcgen05/TMEM/TMA layer kernel (production engine)      */
+
+typedef struct fps_ctx fps_ctx;
+
+/* Host-side view of the reference state_dict (model.py:124-130, :53; key names in SURVEY 2 #5).
+ * All pointers are HOST float32, row-major, torch nn.Linear convention weight[out][in].        */
+typedef struct fps_weights {
+  const float* h_freqs;        /* mapping.freqs         (2, 200)                               */
+  const float* h_coefficients; /* mapping.coefficients  (200)                                  */
+  const float* h_biases;       /* mapping.biases        (200)                                  */
+  const float* h_w0;           /* mapping.linear.weight (700, 400)                             */
+  const float* h_b0;           /* mapping.linear.bias   (700)                                  */
+  const float* h_wh[FPS_NHIDDEN]; /* model.{1,4,7,10,13}.weight (700, 700)                     */
+  const float* h_bh[FPS_NHIDDEN]; /* model.{1,4,7,10,13}.bias   (700)                          */
+} fps_weights;
+
+const char* fps_last_error(void);
+int fps_version(void);
+
+/* Replaces Solver.build_model (solver.py:137-151): uploads + packs the weights on `device`,
+ * allocates the activation workspace for `chunk_points` collocation points per launch wave
+ * (0 = default).  engine = FPS_ENGINE_*.                                                       */
+int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points, int engine);
+int fps_destroy(fps_ctx* ctx);
+int fps_set_engine(fps_ctx* ctx, int engine);
+int fps_get_engine(const fps_ctx* ctx);
+size_t fps_workspace_bytes(const fps_ctx* ctx);
+
+/* Replaces PINN.h (model.py:74-79, :134-146) + calculate_laplace (utils.py:54-68) as called from
+ * Solver.evaluate_network_pde / evaluate_network_bc (solver.py:162-178).
+ * x, y: n float64 coordinates.  H: (n, ld) float32 out.  DH: (n, ld) float32 out or NULL
+ * (NULL = value-only evaluation for boundary points, solver.py:174-175).  ld >= FPS_FP.        */
+int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n,
+                 float* H, float* DH, int64_t ld, void* stream);
+
+/* Replaces `DH.t() @ DH` (solver.py:167).  G64 (FPS_FP, FPS_FP) float64 += A^T A over the n rows
+ * of A (n, ld) float32; both triangles are written.  Accumulating (beta = 1) so that callers can
+ * chunk or shard rows; zero G64 first.                                                          */
+int fps_gram_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* G64, void* stream);
+
+/* Replaces `Ht_bc @ ones` (solver.py:176-178): s64 (FPS_FP) float64 += column sums of A.        */
+int fps_colsum_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* s64, void* stream);
+
+/* Replaces precompute_LHS_RHS (solver.py:187-199) and the LU inside torch.linalg.solve
+ * (solver.py:305):  for every lambda
+ *     LHS = lambda/N * G + ( Gbc - s s^T / N_bc ) / N_bc          (centering matrix folded in)
+ * then the in-place lower Cholesky factor L of LHS is left in L64[(i), :, :] (n_lambda, FPS_FP,
+ * FPS_FP) float64 (mirrored into the upper triangle).  h_lambdas / h_jitter are HOST arrays of
+ * n_lambda entries; h_jitter (may be NULL = 0) is an absolute diagonal shift added to LHS - the
+ * matrix has cond ~1e15 and is exactly singular when N + N_bc < 700, so the caller starts at 0 and
+ * raises the shift only when info reports a breakdown.  info (device int[n_lambda]) receives 0 or
+ * the 1-based index of the first pivot <= eps * max_diag.                                        */
+int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, const double* s64,
+                        int64_t n_total, int64_t nbc_total, const double* h_lambdas,
+                        const double* h_jitter, int n_lambda, double* L64, int* info, void* stream);
+
+/* Replaces `RHSs @ f` (solver.py:197 + :301) for B right-hand sides at once:
+ * R64 (FPS_FP, ldr) float64 += DH^T F,  DH (n, ld) float32,  F (n, ldf) float32, B columns.
+ * Accumulating so that row shards / chunks can be summed; zero R64 first.                       */
+int fps_project_rhs(fps_ctx* ctx, const float* DH, int64_t n, int64_t ld, const float* F, int64_t ldf,
+                    int B, double* R64, int64_t ldr, void* stream);
+
+/* Replaces torch.linalg.solve + the bias formula (solver.py:305-306) for B right-hand sides:
+ *     W = (L L^T)^-1 (scale * R),   bias_j = -( s^T W_j - sum_bc_j ) / N_bc
+ * R64 (FPS_FP, ldr) float64 in, W64 (FPS_FP, ldr) float64 out (may alias R64), sum_bc64 (B),
+ * bias64 (B).  scale = lambda / N.                                                             */
+int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64_t ldr, int B,
+                       double scale, const double* s64, const double* sum_bc64, int64_t nbc_total,
+                       double* W64, double* bias64, void* stream);
+
+/* Replaces the three GEMVs of solver.py:327-330 for B right-hand sides:
+ *     out[i, j] = sum_k A[i, k] W[k, j] + (bias ? bias[j] : 0)       i < n, j < B
+ * A (n, ld) float32 (H, DH or H_bc), W64 (FPS_FP, ldw) float64, out (n, ldo) float32.           */
+int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
+                    const double* bias64, int B, float* out, int64_t ldo, void* stream);
+
+/* Multi-lambda loss of solver.py:312-314 for one lambda: loss64[0] = mean((pred-ref)^2).        */
+int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPS_SM100_H */

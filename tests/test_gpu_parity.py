@@ -1,0 +1,256 @@
+"""GPU: parity of the CUDA path (through the C ABI / the Solver) against the CPU oracle and the
+golden vectors minted from the reference.  Tolerances: north_star asks u within 1e-5 relative L2 of
+the reference (fp64 reference run = the well-defined arithmetic)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import fps_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["simt", "tcgen05"]
+TOL_FEATURE = 2e-6   # fp32-grade features vs fp64 oracle (reference fp32 itself sits at 5e-7 / 9e-7)
+TOL_U = 1e-5         # north_star parity bar
+
+
+@pytest.fixture(scope="module")
+def solver_factory():
+    from fast_poisson_solver_b200 import Solver
+
+    made = []
+
+    def make(**kw):
+        kw.setdefault("use_weights", False)
+        s = Solver(**kw)
+        made.append(s)
+        return s
+
+    yield make
+    made.clear()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_features_vs_reference_golden(golden, solver_factory, engine):
+    g = golden("features_seed0.npz")
+    s = solver_factory(engine=engine)
+    x = torch.tensor(g["x"], device="cuda")
+    y = torch.tensor(g["y"], device="cuda")
+    H, DH = s._features(x, y, True)
+    Hb, none = s._features(x, y, False)
+    torch.cuda.synchronize()
+    assert none is None
+    H, DH, Hb = H.cpu().numpy(), DH.cpu().numpy(), Hb.cpu().numpy()
+    assert np.all(H[:, 700:] == 0) and np.all(DH[:, 700:] == 0) and np.all(Hb[:, 700:] == 0)
+    assert o.rel_l2(H[:, :700], g["H_f64"]) < TOL_FEATURE
+    assert o.rel_l2(DH[:, :700], g["DH_f64"]) < TOL_FEATURE
+    assert o.rel_l2(Hb[:, :700], g["H_f64"]) < TOL_FEATURE
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n", [1, 127, 129, 1000, 20000])
+def test_features_ragged_sizes_vs_oracle(weights0, solver_factory, engine, n):
+    """Tile tails, multi-wave chunks (chunk_points=4096 -> 5 waves at n=20000)."""
+    rng = np.random.default_rng(n)
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    s = solver_factory(engine=engine, chunk_points=4096)
+    H, DH = s._features(torch.tensor(x, device="cuda"), torch.tensor(y, device="cuda"), True)
+    Hr, DHr = o.features_forward(x, y, weights0, np.float64)
+    assert o.rel_l2(H[:, :700].cpu().numpy(), Hr) < TOL_FEATURE
+    assert o.rel_l2(DH[:, :700].cpu().numpy(), DHr) < TOL_FEATURE
+    # per-point error, so that a single bad tile cannot hide in the norm
+    err = np.linalg.norm(DH[:, :700].cpu().numpy() - DHr, axis=1) / np.linalg.norm(DHr, axis=1)
+    assert err.max() < 2e-5
+
+
+def test_engines_agree_on_large_batch(solver_factory):
+    n = 50000
+    rng = np.random.default_rng(5)
+    x = torch.tensor(rng.uniform(0, 1, n), device="cuda")
+    y = torch.tensor(rng.uniform(0, 1, n), device="cuda")
+    a = solver_factory(engine="simt")._features(x, y, True)
+    b = solver_factory(engine="tcgen05")._features(x, y, True)
+    for u, v in zip(a, b):
+        assert o.rel_l2(u.cpu().numpy(), v.cpu().numpy()) < 2e-6
+
+
+def test_gram_colsum_project_reconstruct_kernels(solver_factory):
+    """The fp64-accumulating kernels against numpy fp64 on the same fp32 inputs: exact to rounding."""
+    from fast_poisson_solver_b200 import _lib
+
+    s = solver_factory(engine="simt")
+    lib, ctx, st = s._lib, s._ctx, s._stream()
+    rng = np.random.default_rng(0)
+    for n in (1, 33, 700, 5000):
+        A = torch.zeros((n, 704), dtype=torch.float32, device="cuda")
+        A[:, :700] = torch.tensor(rng.standard_normal((n, 700)), dtype=torch.float32)
+        G = torch.zeros((704, 704), dtype=torch.float64, device="cuda")
+        sv = torch.zeros(704, dtype=torch.float64, device="cuda")
+        _lib.check(lib.fps_gram_accum(ctx, A.data_ptr(), n, 704, G.data_ptr(), st), "gram")
+        _lib.check(lib.fps_colsum_accum(ctx, A.data_ptr(), n, 704, sv.data_ptr(), st), "colsum")
+        A64 = A.double().cpu().numpy()
+        assert np.allclose(G.cpu().numpy(), A64.T @ A64, rtol=1e-13, atol=1e-12)
+        assert np.allclose(sv.cpu().numpy(), A64.sum(0), rtol=1e-13, atol=1e-12)
+        for B in (1, 3, 8, 9, 64, 130):
+            Fm = torch.tensor(rng.standard_normal((n, B)), dtype=torch.float32, device="cuda")
+            R = torch.zeros((704, B), dtype=torch.float64, device="cuda")
+            _lib.check(lib.fps_project_rhs(ctx, A.data_ptr(), n, 704, Fm.data_ptr(), B, B, R.data_ptr(), B, st), "proj")
+            assert np.allclose(R.cpu().numpy(), A64.T @ Fm.double().cpu().numpy(), rtol=1e-13, atol=1e-11), (n, B)
+            W = torch.tensor(rng.standard_normal((704, B)), dtype=torch.float64, device="cuda")
+            bias = torch.tensor(rng.standard_normal(B), dtype=torch.float64, device="cuda")
+            out = torch.empty((n, B), dtype=torch.float32, device="cuda")
+            _lib.check(lib.fps_reconstruct(ctx, A.data_ptr(), n, 704, W.data_ptr(), B, bias.data_ptr(), B,
+                                           out.data_ptr(), B, st), "recon")
+            ref = A64 @ W.cpu().numpy() + bias.cpu().numpy()[None]
+            assert np.allclose(out.cpu().numpy(), ref.astype(np.float32), rtol=2e-7, atol=1e-5), (n, B)
+
+
+def test_cholesky_and_batched_solve_kernels(solver_factory):
+    import ctypes as C
+    from fast_poisson_solver_b200 import _lib
+
+    s = solver_factory(engine="simt")
+    lib, ctx, st = s._lib, s._ctx, s._stream()
+    rng = np.random.default_rng(1)
+    n, nbc = 3000, 200
+    A = rng.standard_normal((n, 700))
+    Hb = rng.standard_normal((nbc, 700))
+    G = np.zeros((704, 704)); G[:700, :700] = A.T @ A
+    Gb = np.zeros((704, 704)); Gb[:700, :700] = Hb.T @ Hb
+    sv = np.zeros(704); sv[:700] = Hb.sum(0)
+    lam = [0.5, 2.0]
+    dG, dGb, dsv = (torch.tensor(v, device="cuda") for v in (G, Gb, sv))
+    L = torch.empty((2, 704, 704), dtype=torch.float64, device="cuda")
+    info = torch.ones(2, dtype=torch.int32, device="cuda")
+    _lib.check(lib.fps_assemble_factor(ctx, dG.data_ptr(), dGb.data_ptr(), dsv.data_ptr(), n, nbc,
+                                       (C.c_double * 2)(*lam), None, 2, L.data_ptr(), info.data_ptr(), st), "factor")
+    assert info.cpu().tolist() == [0, 0]
+    for i, l in enumerate(lam):
+        LHS = l / n * G[:700, :700] + (Gb[:700, :700] - np.outer(sv[:700], sv[:700]) / nbc) / nbc
+        Lr = np.linalg.cholesky(LHS)
+        Ld = L[i].cpu().numpy()
+        assert np.allclose(np.tril(Ld[:700, :700]), Lr, rtol=1e-10, atol=1e-12)
+        assert np.allclose(Ld, Ld.T)  # mirrored
+        assert np.allclose(Ld[700:, 700:], np.eye(4))
+        for B in (1, 5, 8, 19):
+            R = np.zeros((704, B)); R[:700] = rng.standard_normal((700, B))
+            sb = rng.standard_normal(B)
+            dR, dsb = torch.tensor(R, device="cuda"), torch.tensor(sb, device="cuda")
+            W = torch.empty((704, B), dtype=torch.float64, device="cuda")
+            bias = torch.empty(B, dtype=torch.float64, device="cuda")
+            _lib.check(lib.fps_solve_factored(ctx, L[i].data_ptr(), dR.data_ptr(), B, B, 0.25, dsv.data_ptr(),
+                                              dsb.data_ptr(), nbc, W.data_ptr(), bias.data_ptr(), st), "solve")
+            Wr = np.linalg.solve(LHS, 0.25 * R[:700])
+            assert np.allclose(W.cpu().numpy()[:700], Wr, rtol=1e-8, atol=1e-10)
+            assert np.allclose(bias.cpu().numpy(), -(sv[:700] @ Wr - sb) / nbc, rtol=1e-8, atol=1e-10)
+    # a singular matrix must be reported, not produce NaNs
+    _lib.check(lib.fps_assemble_factor(ctx, torch.zeros_like(dG).data_ptr(), dGb.data_ptr(), dsv.data_ptr(), n, nbc,
+                                       (C.c_double * 1)(1.0), None, 1, L.data_ptr(), info.data_ptr(), st), "factor")
+    assert info.cpu().tolist()[0] > 0 and torch.isfinite(L[0]).all()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["solve_G32_seed0.npz", "solve_G100_seed0.npz"])
+def test_solver_vs_reference_golden(golden, solver_factory, engine, name):
+    """BASELINE config 1 shape: unit-square grid, sin source, constant Dirichlet BC; drop-in API."""
+    if not os.path.exists(os.path.join(GOLDEN, name)):
+        pytest.skip(f"{name} not minted")
+    g = golden(name)
+    xp, yp, xb, yb = o.grid_problem(int(g["G"]))
+    s = solver_factory(engine=engine)
+    s.precompute(xp, yp, xb, yb)
+    u, u_pde, u_bc, f_pred, rt = s.solve(g["f"], g["bc"])
+    N, Nbc = xp.size, xb.size
+    assert u.shape == (N + Nbc, 1) and u_pde.shape == (N, 1) and u_bc.shape == (Nbc, 1) and f_pred.shape == (N, 1)
+    assert isinstance(rt, float) and u.dtype == torch.float32 and u.is_cuda
+    assert s.NO == N and s.NdO == Nbc and s.H.shape == (N, 700) and s.w_out.shape == (700, 1)
+    e_u = o.rel_l2(u.cpu().numpy(), g["u_f64"])
+    e_f = o.rel_l2(f_pred.cpu().numpy(), g["f_pred_f64"])
+    floor = o.rel_l2(g["u_f32"], g["u_f64"])
+    print(f"\n[{name} {engine}] u rel-L2 vs reference fp64 = {e_u:.3e} (reference fp32 vs fp64 = {floor:.3e}); f_pred {e_f:.3e}; jitter {s.jitter}")
+    assert e_u < TOL_U
+    assert e_f < 1e-4
+    assert o.rel_l2(s.DHtDH.cpu().numpy()[::7, ::7], g["DHtDH_s7_f64"]) < 5e-6
+    assert o.rel_l2(s.Ht_bc_ones.cpu().numpy(), g["Ht_bc_ones_f64"]) < 2e-6
+    assert o.rel_l2(s.LHSs[0].cpu().numpy()[::7, ::7], g["LHS_s7_f64"]) < 5e-6
+
+
+def test_multilambda_vs_reference_golden(golden, solver_factory):
+    g = golden("solve_G32_ml_seed0.npz")
+    xp, yp, xb, yb = o.grid_problem(int(g["G"]))
+    s = solver_factory(engine="simt", lambdas_pde=list(g["lambdas"]))
+    s.precompute(xp, yp, xb, yb)
+    u = s.solve(g["f"], g["bc"])[0]
+    assert s.lambda_pde == float(g["lambda_f64"])
+    assert o.rel_l2(u.cpu().numpy(), g["u_f64"]) < TOL_U
+    assert np.all(s.Ls > 0)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_batched_solve_vs_oracle_column_loop(weights0, solver_factory, engine):
+    """Batched RHS (extension): oracle = the reference algebra looped over columns."""
+    G = 40
+    xp, yp, xb, yb = o.grid_problem(G)
+    B = 11
+    Fm = np.stack([o.sine_source(xp, yp, seed=j) for j in range(B)], axis=1)
+    bcv = np.random.default_rng(0).uniform(-10, 10, B)
+    BC = np.tile(bcv[None], (xb.size, 1))
+    st = o.precompute(xp, yp, xb, yb, weights0)
+    U, Fp = o.solve_batch(st, Fm, BC)
+    s = solver_factory(engine=engine)
+    s.precompute(xp, yp, xb, yb)
+    u, u_pde, u_bc, f_pred, _ = s.solve(Fm, BC)
+    assert u.shape == (xp.size + xb.size, B) and f_pred.shape == (xp.size, B)
+    for j in range(B):
+        assert o.rel_l2(u[:, j].cpu().numpy(), U[:, j]) < TOL_U, j
+    u2 = s.solve(Fm, bcv)[0]  # constants form
+    assert torch.equal(u, u2)
+    u1 = s.solve(Fm[:, 3], BC[:, 3])[0]
+    assert o.rel_l2(u1.cpu().numpy(), u[:, [3]].cpu().numpy()) < 1e-6
+
+
+def test_input_forms_and_errors(solver_factory):
+    xp, yp, xb, yb = o.grid_problem(28)
+    s = solver_factory(engine="simt")
+    with pytest.raises(AssertionError, match="x coordinates should be in"):
+        s.precompute(xp + 0.5, yp, xb, yb)
+    with pytest.raises(AssertionError, match="y coordinates should be in"):
+        s.precompute(xp, yp - 0.5, xb, yb)
+    f = np.sin(xp * 3) * 10
+    s.precompute(list(xp), torch.tensor(yp), xb.reshape(2, -1), torch.tensor(yb, dtype=torch.float32))
+    a = s.solve(list(f), list(np.full(xb.size, 2.0)))[0]
+    b = s.solve(torch.tensor(f).reshape(28, 28), torch.full((xb.size, 1), 2.0))[0]
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        s.solve(f[:-1], np.zeros(xb.size))
+
+
+def test_rank_deficient_fixture_shape_does_not_crash(solver_factory):
+    """The reference's own test fixture (grid_num=5: 49 equations, 700 unknowns) is singular; the
+    reference returns an arbitrary finite LU answer.  We must return finite numbers too."""
+    xp, yp, xb, yb = o.grid_problem(5)
+    s = solver_factory(engine="simt")
+    s.precompute(xp, yp, xb, yb)
+    u, _, u_bc, f_pred, _ = s.solve(np.ones(25), np.full(xb.size, 1.5))
+    assert torch.isfinite(u).all() and torch.isfinite(f_pred).all()
+    assert any(s.jitter)
+    assert o.rel_l2(f_pred.cpu().numpy(), np.ones(25)) < 1e-3
+    assert abs(u_bc.mean().item() - 1.5) < 1e-3
+
+
+def test_save_load_roundtrip(solver_factory):
+    xp, yp, xb, yb = o.grid_problem(30)
+    f = o.sine_source(xp, yp, seed=3)
+    s = solver_factory(engine="simt")
+    s.precompute(xp, yp, xb, yb, name="rt_case", save=True)
+    assert os.path.isfile(s.precompute_file)
+    u0 = s.solve(f, np.zeros(xb.size))[0]
+    s2 = solver_factory(engine="simt")
+    s2.precompute(xp, yp, xb, yb, name="rt_case", load=True)
+    assert torch.equal(s2.solve(f, np.zeros(xb.size))[0], u0)
+    os.remove(s.precompute_file)
+    s2.precompute(xp, yp, xb, yb, name="rt_case", load=True)  # missing file -> silently recompute
+    assert torch.equal(s2.solve(f, np.zeros(xb.size))[0], u0)

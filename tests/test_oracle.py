@@ -1,0 +1,86 @@
+"""CPU: the oracle restatement against golden vectors minted from the unmodified reference
+(oracle/make_golden.py).  These tests are what pins the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import fps_oracle as o
+
+
+def _digest(w):
+    h = hashlib.sha256()
+    for k in sorted(w):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(w[k]).tobytes())
+    return h.hexdigest()
+
+
+def test_default_init_matches_reference_pinn(golden, weights0):
+    g = golden("features_seed0.npz")
+    assert _digest(weights0) == str(g["weights_sha256"])
+
+
+def test_features_forward_vs_reference_autograd_fp64(golden, weights0):
+    g = golden("features_seed0.npz")
+    H, DH = o.features_forward(g["x"], g["y"], weights0, np.float64)
+    assert o.rel_l2(H, g["H_f64"]) < 1e-13
+    assert o.rel_l2(DH, g["DH_f64"]) < 1e-13
+
+
+def test_features_forward_fp32_noise_floor(golden, weights0):
+    g = golden("features_seed0.npz")
+    H, DH = o.features_forward(g["x"], g["y"], weights0, np.float32)
+    assert o.rel_l2(H, g["H_f64"]) < 3e-6
+    assert o.rel_l2(DH, g["DH_f64"]) < 3e-6
+
+
+def test_autograd_port_matches_reference(golden, weights0):
+    g = golden("features_seed0.npz")
+    H, DH = o.features_autograd(g["x"][:4], g["y"][:4], weights0, np.float64)
+    assert o.rel_l2(H, g["H_f64"][:4]) < 1e-13
+    assert o.rel_l2(DH, g["DH_f64"][:4]) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["solve_G32_seed0.npz", "solve_G100_seed0.npz"])
+def test_precompute_solve_vs_reference_fp64(golden, weights0, name):
+    import os
+    from conftest import GOLDEN
+
+    if not os.path.exists(os.path.join(GOLDEN, name)):
+        pytest.skip(f"{name} not minted")
+    g = golden(name)
+    G = int(g["G"])
+    xp, yp, xb, yb = o.grid_problem(G)
+    st = o.precompute(xp, yp, xb, yb, weights0, dtype=np.float64)
+    u, _, _, f_pred, _, bias = o.solve(st, g["f"], g["bc"])
+    assert o.rel_l2(st.DHtDH[::7, ::7], g["DHtDH_s7_f64"]) < 1e-12
+    assert o.rel_l2(st.LHSs[0][::7, ::7], g["LHS_s7_f64"]) < 1e-10
+    assert o.rel_l2(st.Ht_bc_ones, g["Ht_bc_ones_f64"]) < 1e-13
+    # u is insensitive to the ill-conditioned directions of w (cond ~1e15): 1e-6 is the
+    # reproducibility of the reference fp64 solve itself under re-association
+    assert o.rel_l2(u, g["u_f64"]) < 1e-6
+    assert o.rel_l2(f_pred, g["f_pred_f64"]) < 1e-5
+
+
+def test_multilambda_vs_reference(golden, weights0):
+    g = golden("solve_G32_ml_seed0.npz")
+    xp, yp, xb, yb = o.grid_problem(int(g["G"]))
+    st = o.precompute(xp, yp, xb, yb, weights0, lambdas=list(g["lambdas"]), dtype=np.float64)
+    u = o.solve(st, g["f"], g["bc"])[0]
+    assert o.rel_l2(u, g["u_f64"]) < 1e-6
+
+
+def test_solve_batch_is_column_loop(weights0):
+    xp, yp, xb, yb = o.grid_problem(30)
+    st = o.precompute(xp, yp, xb, yb, weights0)
+    F = np.stack([o.sine_source(xp, yp, seed=s) for s in range(3)], axis=1)
+    BC = np.tile(np.array([[1.0, -2.0, 0.5]]), (xb.size, 1))
+    U, Fp = o.solve_batch(st, F, BC)
+    u1 = o.solve(st, F[:, 1], BC[:, 1])[0]
+    assert np.array_equal(U[:, [1]], u1)
+
+
+def test_range_assert(weights0):
+    with pytest.raises(AssertionError, match="x coordinates should be in"):
+        o.precompute([0.5, 1.5], [0.5, 0.5], [0.0], [0.0], weights0)
