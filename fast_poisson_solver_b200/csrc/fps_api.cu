@@ -16,9 +16,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// Pad a (rows x cols) torch weight[out][in] to (FP x Kp), split into TF32 hi/lo planes on the host.
+// Pad a (rows x cols) torch weight[out][in] to (FPW x Kp), split into TF32 hi/lo planes on the host.
 static int upload_layer(Layer& L, const float* w, const float* b, int cols, int Kp) {
-  std::vector<float> hi((size_t)FP * Kp, 0.f), lo((size_t)FP * Kp, 0.f), bias(FP, 0.f);
+  std::vector<float> hi((size_t)FPW * Kp, 0.f), lo((size_t)FPW * Kp, 0.f), bias(FPW, 0.f);
   for (int r = 0; r < F; ++r) {
     for (int c = 0; c < cols; ++c) {
       const float v = w[(size_t)r * cols + c];
@@ -33,13 +33,13 @@ static int upload_layer(Layer& L, const float* w, const float* b, int cols, int 
     bias[r] = b[r];
   }
   L.Kp = Kp;
-  const size_t bytes = (size_t)FP * Kp * sizeof(float);
+  const size_t bytes = (size_t)FPW * Kp * sizeof(float);
   FPS_CUDA(cudaMalloc(&L.w_hi, bytes));
   FPS_CUDA(cudaMalloc(&L.w_lo, bytes));
-  FPS_CUDA(cudaMalloc(&L.bias, FP * sizeof(float)));
+  FPS_CUDA(cudaMalloc(&L.bias, FPW * sizeof(float)));
   FPS_CUDA(cudaMemcpy(L.w_hi, hi.data(), bytes, cudaMemcpyHostToDevice));
   FPS_CUDA(cudaMemcpy(L.w_lo, lo.data(), bytes, cudaMemcpyHostToDevice));
-  FPS_CUDA(cudaMemcpy(L.bias, bias.data(), FP * sizeof(float), cudaMemcpyHostToDevice));
+  FPS_CUDA(cudaMemcpy(L.bias, bias.data(), FPW * sizeof(float), cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -13,6 +13,7 @@ namespace fps {
 
 constexpr int F = FPS_F;          // 700 features
 constexpr int FP = FPS_FP;        // padded feature dimension (row stride of every activation)
+constexpr int FPW = 768;          // weight rows padded to 6 x 128 (UMMA M tiles); rows >= F are zero
 constexpr int K0 = FPS_K0;        // 400 Fourier inputs
 constexpr int K0P = 416;          // K0 padded to a multiple of 32 (one 128-byte TMA/UMMA K-chunk)
 constexpr int NFREQ = FPS_NFREQ;  // 200
@@ -30,9 +31,9 @@ struct ActPlanes {
 };
 
 struct Layer {
-  float* w_hi;   // (FP, Kp) row-major, K-major == torch weight[out][in], zero padded
+  float* w_hi;   // (FPW, Kp) row-major, K-major == torch weight[out][in], zero padded
   float* w_lo;
-  float* bias;   // (FP) zero padded
+  float* bias;   // (FPW) zero padded
   int Kp;        // padded K (K0P for layer 0, FP otherwise)
 };
 
@@ -102,6 +103,19 @@ int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cud
 
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// tanh layer on the four forward-mode streams (the closed form of what
+// utils.py:54-68 obtains by autograd):  h = tanh a, d1 = 1-h^2, d2 = -2 h d1,
+// h_x = d1 a_x, h_y = d1 a_y, h_lap = d2 (a_x^2 + a_y^2) + d1 a_lap.
+__device__ __forceinline__ void tanh_streams(float a, float ax, float ay, float al, float& h, float& hx, float& hy,
+                                             float& hl) {
+  h = tanhf(a);
+  const float d1 = fmaf(-h, h, 1.0f);
+  const float d2 = -2.0f * h * d1;
+  hx = d1 * ax;
+  hy = d1 * ay;
+  hl = fmaf(d2, fmaf(ax, ax, ay * ay), d1 * al);
+}
 
 __device__ __forceinline__ void split_store(float* hi, float* lo, float v) {
   float h = tf32_hi(v);

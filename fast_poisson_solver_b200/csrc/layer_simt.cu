@@ -14,16 +14,6 @@ namespace fps {
 
 constexpr int SBM = 128, SBN = 64, SBK = 16, STHREADS = 256;
 
-__device__ __forceinline__ void tanh_streams(float a, float ax, float ay, float al, float& h, float& hx, float& hy,
-                                             float& hl) {
-  h = tanhf(a);
-  const float d1 = fmaf(-h, h, 1.0f);
-  const float d2 = -2.0f * h * d1;
-  hx = d1 * ax;
-  hy = d1 * ay;
-  hl = fmaf(d2, fmaf(ax, ax, ay * ay), d1 * al);
-}
-
 template <int S, bool LAST>
 __global__ void __launch_bounds__(STHREADS)
 layer_simt_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int Kp,
