@@ -52,7 +52,12 @@ SIGNATURES = {
     "fps_solve_factored": (_i32, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "fps_reconstruct": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "fps_mse": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "fps_launch_count": (_i64, []),
+    "fps_profile_enable": (_i32, [_vp, _i32]),
+    "fps_profile_reset": (_i32, [_vp]),
+    "fps_profile_read": (_i32, [_vp, _i32, C.POINTER(_f64), C.POINTER(_i64)]),
 }
+PROF_KINDS = ["fourier", "layer0", "hidden", "last", "gram", "factor", "project", "trisolve", "reconstruct"]
 
 _lib = None
 

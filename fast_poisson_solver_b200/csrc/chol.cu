@@ -198,6 +198,7 @@ int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gb
     }
     chol_fixup_kernel<<<CN, 256, 0, st>>>(Ll, Dfac);
   }
+  count_launch(n_lambda * (3 + CNB + (CNB - 1)));
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -313,6 +314,7 @@ int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, 
   }
   solve_factored_kernel<<<(B + SC - 1) / SC, 256, smem, st>>>(L, R, ldr, B, scale, s, sum_bc, 1.0 / (double)nbc_total,
                                                               W, bias);
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -65,6 +65,7 @@ int launch_fourier(const fps_ctx* ctx, const double* x, const double* y, int64_t
     fourier_kernel<4><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out.hi, out.lo);
   else
     fourier_kernel<1><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out.hi, out.lo);
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -3,11 +3,55 @@
 #include "fps_common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <utility>
 #include <vector>
 
 namespace fps {
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+
+// Event-pair recorder: one (start, stop) pair per instrumented region, pooled and reused.
+struct Prof {
+  bool on = false;
+  struct Rec { int kind; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  double ms[FPS_PROF_KINDS] = {0};
+  long long n[FPS_PROF_KINDS] = {0};
+  cudaEvent_t begin(int kind, cudaStream_t st) {
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    recs.push_back({kind, ev.first, ev.second});
+    cudaEventRecord(ev.first, st);
+    return ev.second;
+  }
+  void collect() {
+    for (auto& r : recs) {
+      cudaEventSynchronize(r.b);
+      float t = 0.f;
+      cudaEventElapsedTime(&t, r.a, r.b);
+      ms[r.kind] += t;
+      n[r.kind] += 1;
+      pool.push_back({r.a, r.b});
+    }
+    recs.clear();
+  }
+  ~Prof() {
+    collect();
+    for (auto& e : pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  }
+};
+
+struct ProfScope {
+  cudaEvent_t stop = nullptr;
+  cudaStream_t st;
+  ProfScope(const fps_ctx* ctx, int kind, cudaStream_t s) : st(s) {
+    if (ctx->prof && ctx->prof->on) stop = ctx->prof->begin(kind, s);
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -67,10 +111,12 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
               device, prop.major, prop.minor);
   fps_ctx* ctx = new fps_ctx();
   memset(ctx, 0, sizeof(*ctx));
+  ctx->prof = new Prof();
   ctx->device = device;
   ctx->engine = engine;
   ctx->sm_count = prop.multiProcessorCount;
-  ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 16384;
+  // default wave: 296 row tiles x 6 feature tiles = 1776 = 12 x 148 CTA tiles (no tail wave on B200)
+  ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 18944;
   int rc = upload_layer(ctx->layer[0], w->h_w0, w->h_b0, K0, K0P);
   for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer(ctx->layer[l + 1], w->h_wh[l], w->h_bh[l], F, FP);
   if (rc) { fps_destroy(ctx); return rc; }
@@ -111,6 +157,7 @@ int fps_destroy(fps_ctx* ctx) {
     cudaFree(ctx->act[i].lo);
   }
   cudaFree(ctx->partial);
+  delete ctx->prof;
   delete ctx;
   return 0;
 }
@@ -136,12 +183,16 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
   for (int64_t p0 = 0; p0 < n; p0 += wave) {
     const int64_t np = (n - p0 < wave) ? n - p0 : wave;
     int cur = 0;
-    if (int rc = launch_fourier(ctx, x + p0, y + p0, np, streams, ctx->act[cur], st)) return rc;
+    {
+      ProfScope ps(ctx, FPS_PROF_FOURIER, st);
+      if (int rc = launch_fourier(ctx, x + p0, y + p0, np, streams, ctx->act[cur], st)) return rc;
+    }
     for (int l = 0; l < NLAYER; ++l) {
       const bool last = (l == NLAYER - 1);
       float* Hc = H + p0 * ld;
       float* DHc = DH ? DH + p0 * ld : nullptr;
       int rc;
+      ProfScope ps(ctx, l == 0 ? FPS_PROF_LAYER0 : (last ? FPS_PROF_LAST : FPS_PROF_HIDDEN), st);
       if (ctx->engine == FPS_ENGINE_TCGEN05)
         rc = launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, streams, last, Hc, DHc, ld, st);
       else
@@ -156,6 +207,7 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
 int fps_gram_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* G64, void* stream) {
   FPS_REQUIRE(ctx && A && G64, "fps_gram_accum: null argument");
   FPS_REQUIRE(ld >= FP, "fps_gram_accum: ld=%lld < %d", (long long)ld, FP);
+  ProfScope ps(ctx, FPS_PROF_GRAM, (cudaStream_t)stream);
   return launch_atb_f64(ctx, A, ld, FP, A, ld, FP, n, G64, FP, true, (cudaStream_t)stream);
 }
 
@@ -169,6 +221,7 @@ int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, co
                         int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L64,
                         int* info, void* stream) {
   FPS_REQUIRE(ctx && G64 && Gbc64 && s64 && h_lambdas && L64 && info && n_lambda > 0, "fps_assemble_factor: bad argument");
+  ProfScope ps(ctx, FPS_PROF_FACTOR, (cudaStream_t)stream);
   return launch_assemble_factor(ctx, G64, Gbc64, s64, n_total, nbc_total, h_lambdas, h_jitter, n_lambda, L64, info,
                                 (cudaStream_t)stream);
 }
@@ -177,6 +230,7 @@ int fps_project_rhs(fps_ctx* ctx, const float* DH, int64_t n, int64_t ld, const 
                     double* R64, int64_t ldr, void* stream) {
   FPS_REQUIRE(ctx && DH && Fm && R64, "fps_project_rhs: null argument");
   FPS_REQUIRE(ld >= FP && ldf >= B && ldr >= B, "fps_project_rhs: bad leading dimension");
+  ProfScope ps(ctx, FPS_PROF_PROJECT, (cudaStream_t)stream);
   return launch_atb_f64(ctx, DH, ld, FP, Fm, ldf, B, n, R64, ldr, false, (cudaStream_t)stream);
 }
 
@@ -185,6 +239,7 @@ int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64
                        void* stream) {
   FPS_REQUIRE(ctx && L64 && R64 && s64 && sum_bc64 && W64 && bias64, "fps_solve_factored: null argument");
   FPS_REQUIRE(ldr >= B && nbc_total > 0, "fps_solve_factored: bad argument");
+  ProfScope ps(ctx, FPS_PROF_TRISOLVE, (cudaStream_t)stream);
   return launch_solve_factored(L64, R64, ldr, B, scale, s64, sum_bc64, nbc_total, W64, bias64, (cudaStream_t)stream);
 }
 
@@ -192,12 +247,36 @@ int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const d
                     const double* bias64, int B, float* out, int64_t ldo, void* stream) {
   FPS_REQUIRE(ctx && A && W64 && out, "fps_reconstruct: null argument");
   FPS_REQUIRE(ldw >= B && ldo >= B, "fps_reconstruct: bad leading dimension");
+  ProfScope ps(ctx, FPS_PROF_RECONSTRUCT, (cudaStream_t)stream);
   return launch_reconstruct(ctx, A, n, ld, W64, ldw, bias64, B, out, ldo, (cudaStream_t)stream);
 }
 
 int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream) {
   FPS_REQUIRE(ctx && pred && ref && loss64 && n > 0, "fps_mse: bad argument");
   return launch_mse(pred, ref, n, loss64, (cudaStream_t)stream);
+}
+
+int64_t fps_launch_count(void) { return (int64_t)g_launches; }
+
+int fps_profile_enable(fps_ctx* ctx, int on) {
+  FPS_REQUIRE(ctx, "null ctx");
+  ctx->prof->on = on != 0;
+  return 0;
+}
+
+int fps_profile_reset(fps_ctx* ctx) {
+  FPS_REQUIRE(ctx, "null ctx");
+  ctx->prof->collect();
+  for (int k = 0; k < FPS_PROF_KINDS; ++k) { ctx->prof->ms[k] = 0; ctx->prof->n[k] = 0; }
+  return 0;
+}
+
+int fps_profile_read(fps_ctx* ctx, int kind, double* ms, int64_t* launches) {
+  FPS_REQUIRE(ctx && kind >= 0 && kind < FPS_PROF_KINDS && ms && launches, "fps_profile_read: bad argument");
+  ctx->prof->collect();
+  *ms = ctx->prof->ms[kind];
+  *launches = ctx->prof->n[kind];
+  return 0;
 }
 
 }  // extern "C"

@@ -39,7 +39,13 @@ struct Layer {
 
 }  // namespace fps
 
+namespace fps {
+struct Prof;  // event-pair recorder, fps_api.cu
+extern unsigned long long g_launches;  // kernels launched by this library (host-side counter)
+}
+
 struct fps_ctx {
+  fps::Prof* prof;
   int device;
   int engine;
   int chunk;              // points per wave
@@ -100,6 +106,9 @@ int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, 
 int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
                        const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
 int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st);
+
+// count `n` kernel launches (instrumentation for bench.py's gpu_launches)
+inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 
 // ---- small device helpers -------------------------------------------------------------------
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }

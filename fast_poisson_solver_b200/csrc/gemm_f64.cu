@@ -236,6 +236,7 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
     else if (Nc <= 4) { FPS_SMALL(4); }
     else { FPS_SMALL(8); }
 #undef FPS_SMALL
+    count_launch(2);
     FPS_CUDA(cudaGetLastError());
     return 0;
   }
@@ -258,6 +259,7 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
   FPS_CUDA(cudaGetLastError());
   atb_reduce_kernel<<<ntiles, 256, 0, st>>>(ctx->partial, ntiles, (int)slices, tiles_j, symmetric ? 1 : 0, M, Nc, C,
                                             ldc);
+  count_launch(2);
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -279,6 +281,7 @@ __global__ void colsum_kernel(const float* __restrict__ A, int64_t n, int64_t ld
 int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st) {
   if (n <= 0) return 0;
   colsum_kernel<<<FP / 64, 256, 0, st>>>(A, n, ld, s64);
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -417,6 +420,7 @@ int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld
     dim3 grid((unsigned)((n + GT - 1) / GT), (unsigned)((B + GT - 1) / GT));
     nn_f64_kernel<<<grid, GTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
   }
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -444,6 +448,7 @@ __global__ void mse_kernel(const float* __restrict__ pred, const float* __restri
 
 int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st) {
   mse_kernel<<<1, 1024, 0, st>>>(pred, ref, n, loss);
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -142,6 +142,7 @@ int launch_layer_simt(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, in
     if (last) FPS_SIMT_LAUNCH(1, true); else FPS_SIMT_LAUNCH(1, false);
   }
 #undef FPS_SIMT_LAUNCH
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -38,14 +38,18 @@ namespace fps {
 
 constexpr int TM = 128;                 // features per tile  (UMMA M)
 constexpr int TN = 256;                 // activation rows per tile (UMMA N)
-constexpr int TK = 32;                  // fp32 per K chunk = 128 bytes = one swizzle atom row
+#ifndef FPS_TK
+#define FPS_TK 16
+#endif
+constexpr int TK = FPS_TK;              // fp32 per K chunk: 16 -> 64-byte swizzle rows, 32 -> 128-byte
 constexpr int UK = 8;                   // K per tcgen05.mma.kind::tf32
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 64 / TK;      // ring depth: 4 x 48 KiB (TK = 16) or 2 x 96 KiB (TK = 32)
+constexpr int ROW_BYTES = TK * 4;       // shared-memory row = swizzle span
 constexpr int A_BYTES = TM * TK * 4;    // 16 KiB
 constexpr int B_BYTES = TN * TK * 4;    // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 96 KiB
 constexpr int TC_THREADS = 320;       // TMA warp, MMA warp, 8 accumulate/epilogue warps
-constexpr int SEG_CHUNKS = 1;         // K chunks (of 32) accumulated inside the tensor core before promotion
+constexpr int SEG_CHUNKS = 32 / TK;   // K chunks accumulated inside the tensor core before promotion (K = 32)
 constexpr int TMEM_COLS = 512;
 constexpr int N_FEAT_TILES = FPW / TM;  // 6
 constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -95,14 +99,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
+// K-major swizzled shared-memory matrix descriptor: rows of ROW_BYTES (= swizzle span), 8-row groups
+// 8*ROW_BYTES apart.  layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3ffff) >> 4);   // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);         // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;     // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61; // swizzle mode
   return d;
 }
 
@@ -156,9 +161,9 @@ layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + TC_STAGES * STAGE_BYTES;
-  // barrier slots (8 bytes each): full[2], empty[2], tmem_full[2], tmem_empty[2], then the TMEM base word
-  const uint32_t bar_full = bar_base, bar_empty = bar_base + 16, bar_tfull = bar_base + 32, bar_tempty = bar_base + 48;
-  const uint32_t tmem_slot = bar_base + 64;
+  // barrier slots (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base word
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 32, bar_tfull = bar_base + 64, bar_tempty = bar_base + 80;
+  const uint32_t tmem_slot = bar_base + 96;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -173,6 +178,8 @@ layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, 8);  // one arrive per accumulate warp
     }
@@ -335,7 +342,8 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64
   cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for K=%llu rows=%llu", (int)r, (unsigned long long)K,
@@ -409,6 +417,7 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
     if (last) FPS_TC_LAUNCH(1, true); else FPS_TC_LAUNCH(1, false);
   }
 #undef FPS_TC_LAUNCH
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }

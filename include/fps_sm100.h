@@ -113,6 +113,27 @@ int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const d
 /* Multi-lambda loss of solver.py:312-314 for one lambda: loss64[0] = mean((pred-ref)^2).        */
 int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream);
 
+/* ---- instrumentation (bench.py / profiles) ----------------------------------------------------
+ * fps_launch_count: number of kernels this library has launched in this process (all contexts).
+ * fps_profile_enable(ctx, 1): bracket every kernel launch of ctx with CUDA events on its stream.
+ * fps_profile_read: synchronises the recorded events and returns, for kernel class `kind`
+ * (FPS_PROF_*), the summed device time in ms and the number of launches since the last
+ * fps_profile_reset.                                                                            */
+#define FPS_PROF_FOURIER 0
+#define FPS_PROF_LAYER0 1      /* mapping.linear, K = 400                                         */
+#define FPS_PROF_HIDDEN 2      /* hidden 700x700 layers writing the next layer's planes           */
+#define FPS_PROF_LAST 3        /* last hidden layer writing H / DH                                */
+#define FPS_PROF_GRAM 4
+#define FPS_PROF_FACTOR 5
+#define FPS_PROF_PROJECT 6
+#define FPS_PROF_TRISOLVE 7
+#define FPS_PROF_RECONSTRUCT 8
+#define FPS_PROF_KINDS 9
+int64_t fps_launch_count(void);
+int fps_profile_enable(fps_ctx* ctx, int on);
+int fps_profile_reset(fps_ctx* ctx);
+int fps_profile_read(fps_ctx* ctx, int kind, double* ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif
