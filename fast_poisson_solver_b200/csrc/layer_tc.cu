@@ -1,61 +1,67 @@
 // Dense layer + tanh with forward-mode derivative streams on the 5th-gen tensor cores
-// (FPS_ENGINE_TCGEN05): TMA -> 128B-swizzled shared memory -> tcgen05.mma.kind::tf32 (3xTF32 split)
-// -> fp32 accumulators in TMEM -> tcgen05.ld -> fused tanh/derivative epilogue -> next layer's
-// hi/lo planes (or H / DH for the last layer).
+// (FPS_ENGINE_TCGEN05): TMA -> swizzled shared memory -> tcgen05.mma.kind::tf32 (3xTF32 split)
+// -> fp32 segment accumulators in TMEM -> tcgen05.ld -> round-to-nearest running sums in registers
+// -> fused tanh/derivative epilogue -> next layer's hi/lo planes (or H / DH for the last layer).
 //
 // Reference maths: nn.Linear + nn.Tanh (model.py:53-60, :144) and the Laplacian that
 // utils.py:54-68 extracts by 2 800 autograd sweeps, here as closed-form streams.
 //
-// GEMM mapping (per CTA tile):
+// GEMM mapping (per CTA):
 //   D[f, r] = sum_k W[f, k] * Act[r, k]      f: 128 output features  -> UMMA M  (TMEM lanes)
 //                                            r: 256 activation rows  -> UMMA N  (TMEM columns)
-//   A operand = W tile   (128 x 32 fp32, K-major, SWIZZLE_128B)  hi and lo planes
-//   B operand = Act tile (256 x 32 fp32, K-major, SWIZZLE_128B)  hi and lo planes
+//   A operand = W tile   (128 x TK fp32, K-major, swizzled)  hi and lo planes
+//   B operand = Act tile (256 x TK fp32, K-major, swizzled)  hi and lo planes
 //   Activation row r = 4*point + stream, so one thread (= one TMEM lane = one feature) finds the
 //   four streams (v, v_x, v_y, v_lap) of a point in four adjacent TMEM columns and can apply the
 //   tanh recurrences without any cross-thread exchange.
 //   3xTF32:  D += Alo*Bhi + Ahi*Blo + Ahi*Bhi per 8-wide k step (hi = fp32 with the low 13 mantissa
 //   bits cleared, lo = exact remainder; both planes are produced by the previous layer's epilogue).
 //
+// NCTA = 2 (production): two CTAs of a cluster form a tcgen05 pair (cta_group::2, UMMA M = 256).
+//   CTA rank r owns feature tile 2*fp + r; the 256-row activation tile is SHARED: each CTA loads only
+//   128 of its rows and the tensor cores of both SMs read both halves.  That cuts the L2->SM operand
+//   traffic per MMA by a third (64 instead of 96 KiB per K=32), which is what bounds this kernel
+//   (measured: with 1-CTA tiles the tensor pipe sits at 60 % while L2->SM runs at 8.7 TB/s).
+// NCTA = 1: single-CTA variant kept for A/B measurements (FPS_TC_PAIR=0).
 //
 // Accumulation accuracy.  The tensor core truncates (rounds toward zero) when it writes the fp32
 // accumulator, so a single 704-long chain of 264 MMAs biases every output by ~3e-6 per layer
-// (measured: H off by 1.6e-5 after six layers).  The K loop is therefore cut into segments of
-// SEG_CHUNKS x 32: each segment accumulates in TMEM from zero, then the accumulate warps pull it
-// out with tcgen05.ld and add it to a round-to-nearest fp32 running sum held in registers while the
-// tensor core already works on the next segment in the other TMEM buffer.
+// (measured: H off by 1.6e-5 after six layers).  The K loop is therefore cut into segments of 32:
+// each segment accumulates in TMEM from zero, then the accumulate warps pull it out with tcgen05.ld
+// and add it to a round-to-nearest fp32 running sum held in registers while the tensor core already
+// works on the next segment in the other TMEM buffer.
 //
 // Warp roles (320 threads, persistent CTAs, one per SM):
-//   warp 0     TMA producer            (2-stage ring of {Ahi, Alo, Bhi, Blo} = 96 KiB per stage)
-//   warp 1     TMEM allocator + MMA issuer (one elected lane)
+//   warp 0     TMA producer (ring of {Ahi, Alo, Bhi, Blo} K=16 slabs; 4 stages x 48 KiB or 6 x 32 KiB)
+//   warp 1     TMEM allocator + MMA issuer (one elected lane; in a pair only the rank-0 CTA issues)
 //   warps 2-9  accumulate + epilogue; TMEM lane quadrant = warp_id % 4, column half = (warp_id-2)/4,
 //              128 running sums per thread.  The 512 TMEM columns hold two 256-column segment
 //              accumulators (double buffer between MMA issuer and accumulate warps).
 #include "fps_common.cuh"
 #include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
 
 namespace fps {
 
-constexpr int TM = 128;                 // features per tile  (UMMA M)
+constexpr int TM = 128;                 // features per CTA tile (UMMA M per CTA)
 constexpr int TN = 256;                 // activation rows per tile (UMMA N)
-#ifndef FPS_TK
-#define FPS_TK 16
-#endif
-constexpr int TK = FPS_TK;              // fp32 per K chunk: 16 -> 64-byte swizzle rows, 32 -> 128-byte
+constexpr int TK = 16;                  // fp32 per K slab: 64-byte swizzled rows
 constexpr int UK = 8;                   // K per tcgen05.mma.kind::tf32
-constexpr int TC_STAGES = 64 / TK;      // ring depth: 4 x 48 KiB (TK = 16) or 2 x 96 KiB (TK = 32)
-constexpr int ROW_BYTES = TK * 4;       // shared-memory row = swizzle span
-constexpr int A_BYTES = TM * TK * 4;    // 16 KiB
-constexpr int B_BYTES = TN * TK * 4;    // 32 KiB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 96 KiB
-constexpr int TC_THREADS = 320;       // TMA warp, MMA warp, 8 accumulate/epilogue warps
-constexpr int SEG_CHUNKS = 32 / TK;   // K chunks accumulated inside the tensor core before promotion (K = 32)
+constexpr int ROW_BYTES = TK * 4;       // shared-memory row = swizzle span (SWIZZLE_64B)
+constexpr int BOX_ROWS = 128;           // every TMA box is 128 rows x TK
+constexpr int BOX_BYTES = BOX_ROWS * ROW_BYTES;  // 8 KiB
+constexpr int SEG_SLABS = 128 / TK;     // K slabs accumulated inside the tensor core before promotion (K = 128)
+constexpr int TC_THREADS = 320;         // TMA warp, MMA warp, 8 accumulate/epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int N_FEAT_TILES = FPW / TM;  // 6
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int RING_BYTES = 192 * 1024;
+constexpr int TC_SMEM = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int MAX_STAGES = 8;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit: address of the pair leader's copy
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -65,6 +71,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in the pair leader's shared memory (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -89,41 +99,68 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+template <int NCTA>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if (NCTA == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    // executed by both CTAs of the pair; the bytes are accounted on the LEADER's mbarrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major swizzled shared-memory matrix descriptor: rows of ROW_BYTES (= swizzle span), 8-row groups
-// 8*ROW_BYTES apart.  layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+// K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B, 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3ffff) >> 4);         // start address, 16-byte units
   d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
   d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;     // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61; // swizzle mode
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61; // swizzle mode: 2 = 128B, 4 = 64B
   return d;
 }
 
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128 * NCTA, N = 256
+template <int NCTA>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC_TF32), "r"(accumulate)
-      : "memory");
+  constexpr uint32_t idesc =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((TM * NCTA) >> 4) << 24);
+  if (NCTA == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
+// arrive on `bar` (in every CTA of the pair) once all previously issued MMAs have retired
+template <int NCTA>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (NCTA == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+  }
 }
 
 // 32 lanes x 32 consecutive columns -> 32 registers per thread
@@ -141,6 +178,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 struct TcParams {
   const float* bias;
   float* out_hi;
@@ -149,49 +195,65 @@ struct TcParams {
   float* DH;
   int64_t ld;
   int64_t rows;   // valid activation rows = points * S
-  int nk;         // K chunks of 32
+  int nk;         // K slabs of TK
   int row_tiles;  // ceil(rows / 256)
+  int debug;      // FPS_TC_DEBUG experiments (0 = production)
+  int seg;        // K slabs per tensor-core accumulation segment
+  float gain;      // 1 + kappa(K_seg): first-order compensation of the accumulator truncation bias
+  float gain_tail; // same for the shorter last segment of a tile
 };
 
-template <int S, bool LAST>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
-                const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-                const TcParams P) {
+template <int S, bool LAST, int NCTA>
+__device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo,
+                                              const CUtensorMap& tmAhi, const CUtensorMap& tmAlo, const TcParams& P) {
+  constexpr int B_BOXES = TN / BOX_ROWS / NCTA;                   // activation boxes this CTA loads per plane
+  constexpr int STAGE_BYTES = 2 * BOX_BYTES + 2 * B_BOXES * BOX_BYTES;  // {Ahi, Alo, Bhi.., Blo..}
+  constexpr int STAGES = RING_BYTES / STAGE_BYTES;                // 4 (single CTA) or 6 (pair)
+  static_assert(STAGES <= MAX_STAGES, "ring too deep for the barrier block");
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + TC_STAGES * STAGE_BYTES;
-  // barrier slots (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base word
-  const uint32_t bar_full = bar_base, bar_empty = bar_base + 32, bar_tfull = bar_base + 64, bar_tempty = bar_base + 80;
-  const uint32_t tmem_slot = bar_base + 96;
+  const uint32_t bar_base = smem_base + RING_BYTES;
+  // barrier slots (8 bytes each): full[8], empty[8], tmem_full[2], tmem_empty[2], then the TMEM base word
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_tfull = bar_base + 128, bar_tempty = bar_base + 144;
+  const uint32_t tmem_slot = bar_base + 160;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int total_tiles = P.row_tiles * N_FEAT_TILES;
+  const int rank = (NCTA == 2) ? (int)cluster_ctarank() : 0;
+  const int group = blockIdx.x / NCTA, ngroups = gridDim.x / NCTA;
+  constexpr int FT_GROUPS = N_FEAT_TILES / NCTA;  // feature tiles (pairs of tiles) per row tile
+  const int total_tiles = P.row_tiles * FT_GROUPS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAlo)) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 8);  // one arrive per accumulate warp
+      mbar_init(bar_tempty + 8 * s, 8 * NCTA);  // one arrive per accumulate warp of every CTA in the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -199,28 +261,32 @@ layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int ft = t % N_FEAT_TILES, rt = t / N_FEAT_TILES;
+      for (int t = group; t < total_tiles; t += ngroups) {
+        const int ft = (t % FT_GROUPS) * NCTA + rank, rt = t / FT_GROUPS;
+        const int brow = rt * TN + rank * (TN / NCTA);
         for (int kc = 0; kc < P.nk; ++kc) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, STAGE_BYTES);
-          tma_load_2d(sa, &tmWhi, full, kc * TK, ft * TM);
-          tma_load_2d(sa + A_BYTES, &tmWlo, full, kc * TK, ft * TM);
-          tma_load_2d(sa + 2 * A_BYTES, &tmAhi, full, kc * TK, rt * TN);
-          tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmAlo, full, kc * TK, rt * TN);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (rank == 0) mbar_expect_tx(full, STAGE_BYTES * NCTA);
+          tma_load_2d<NCTA>(sa, &tmWhi, full, kc * TK, ft * TM);
+          tma_load_2d<NCTA>(sa + BOX_BYTES, &tmWlo, full, kc * TK, ft * TM);
+#pragma unroll
+          for (int b = 0; b < B_BOXES; ++b) {
+            tma_load_2d<NCTA>(sa + (2 + b) * BOX_BYTES, &tmAhi, full, kc * TK, brow + b * BOX_ROWS);
+            tma_load_2d<NCTA>(sa + (2 + B_BOXES + b) * BOX_BYTES, &tmAlo, full, kc * TK, brow + b * BOX_ROWS);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (pair leader only) =================
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        for (int kc0 = 0; kc0 < P.nk; kc0 += SEG_CHUNKS) {
-          const int kc1 = (kc0 + SEG_CHUNKS < P.nk) ? kc0 + SEG_CHUNKS : P.nk;
+      for (int t = group; t < total_tiles; t += ngroups) {
+        for (int kc0 = 0; kc0 < P.nk; kc0 += P.seg) {
+          const int kc1 = (kc0 + P.seg < P.nk) ? kc0 + P.seg : P.nk;
           mbar_wait(bar_tempty + 8 * abuf, aphase ^ 1);  // accumulate warps have drained this buffer
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + abuf * TN;
@@ -228,20 +294,23 @@ layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_BYTES);
-            const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_BYTES),
-                           b_lo = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+            const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + BOX_BYTES);
+            const uint64_t b_hi = umma_desc(sa + 2 * BOX_BYTES), b_lo = umma_desc(sa + (2 + B_BOXES) * BOX_BYTES);
 #pragma unroll
             for (int j = 0; j < TK / UK; ++j) {
-              const uint64_t adv = (uint64_t)((j * UK * 4) >> 4);  // +32 bytes per k step inside the swizzle atom
-              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, (kc > kc0 || j > 0) ? 1u : 0u);
-              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, 1u);
-              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, 1u);
+              const uint64_t adv = (uint64_t)((j * UK * 4) >> 4);  // +32 bytes per k step inside the swizzle row
+              if (P.debug != 1) {
+                umma_tf32<NCTA>(d_tmem, a_lo + adv, b_hi + adv, (kc > kc0 || j > 0) ? 1u : 0u);
+                umma_tf32<NCTA>(d_tmem, a_hi + adv, b_lo + adv, 1u);
+                umma_tf32<NCTA>(d_tmem, a_hi + adv, b_hi + adv, 1u);
+              } else {
+                umma_tf32<NCTA>(d_tmem, a_hi + adv, b_hi + adv, (kc > kc0 || j > 0) ? 1u : 0u);
+              }
             }
-            umma_commit(bar_empty + 8 * stage);  // smem slot is free once these MMAs retire
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            umma_commit<NCTA>(bar_empty + 8 * stage);  // smem slot is free once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(bar_tfull + 8 * abuf);  // segment accumulator complete
+          umma_commit<NCTA>(bar_tfull + 8 * abuf);  // segment accumulator complete
           if (++abuf == 2) { abuf = 0; aphase ^= 1; }
         }
       }
@@ -251,28 +320,32 @@ layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
     const int quad = warp % 4;          // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
     const int half = (warp - 2) / 4;    // which 128 of the 256 accumulator columns
     uint32_t abuf = 0, aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int ft = t % N_FEAT_TILES, rt = t / N_FEAT_TILES;
+    for (int t = group; t < total_tiles; t += ngroups) {
+      const int ft = (t % FT_GROUPS) * NCTA + rank, rt = t / FT_GROUPS;
       const int f = ft * TM + quad * 32 + lane;  // this thread's output feature
       const bool f_ok = f < FP;                  // features 704..767 are tile padding
       const float bias = P.bias[f];
       float acc[TN / 2];
 #pragma unroll
       for (int i = 0; i < TN / 2; ++i) acc[i] = 0.f;
-      for (int kc0 = 0; kc0 < P.nk; kc0 += SEG_CHUNKS) {
+      for (int kc0 = 0; kc0 < P.nk; kc0 += P.seg) {
         mbar_wait(bar_tfull + 8 * abuf, aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + abuf * TN + half * (TN / 2) + ((uint32_t)(quad * 32) << 16);
+        const float g = (kc0 + P.seg <= P.nk) ? P.gain : P.gain_tail;
 #pragma unroll
         for (int c = 0; c < TN / 64; ++c) {
           float v[32];
+          if (P.debug == 2 && c > 0) continue;
           tmem_ld32(taddr + c * 32, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c * 32 + i] += v[i];  // round-to-nearest promotion
+          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(v[i], g, acc[c * 32 + i]);  // RN promotion + bias gain
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * abuf);
+        if (lane == 0) {
+          if (NCTA == 1) mbar_arrive(bar_tempty + 8 * abuf); else mbar_arrive_leader(bar_tempty + 8 * abuf);
+        }
         if (++abuf == 2) { abuf = 0; aphase ^= 1; }
       }
       const int64_t r0 = (int64_t)rt * TN + half * (TN / 2);
@@ -319,11 +392,30 @@ layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (NCTA == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+template <int S, bool LAST>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                const TcParams P) {
+  layer_tc_body<S, LAST, 1>(tmWhi, tmWlo, tmAhi, tmAlo, P);
+}
+
+template <int S, bool LAST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+layer_tc_pair_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                     const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                     const TcParams P) {
+  layer_tc_body<S, LAST, 2>(tmWhi, tmWlo, tmAhi, tmAlo, P);
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------------------
@@ -334,22 +426,29 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TcState {
   CUtensorMap w_hi[NLAYER], w_lo[NLAYER];
   CUtensorMap act_hi[2][2], act_lo[2][2];  // [buffer][0: K = K0P, 1: K = FP]
+  int pair;
 };
 
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64_t K, uint64_t rows, uint32_t box_rows) {
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64_t K, uint64_t rows) {
   cuuint64_t dims[2] = {K, rows};
   cuuint64_t strides[1] = {K * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)BOX_ROWS};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for K=%llu rows=%llu", (int)r, (unsigned long long)K,
               (unsigned long long)rows);
     return 1;
   }
+  return 0;
+}
+
+template <typename Kern>
+static int set_smem(Kern k) {
+  FPS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   return 0;
 }
 
@@ -361,24 +460,26 @@ int tc_init(fps_ctx* ctx) {
   EncodeTiledFn enc = (EncodeTiledFn)fn;
   TcState* s = new TcState();
   ctx->tc_state = s;
+  s->pair = getenv("FPS_TC_PAIR") ? atoi(getenv("FPS_TC_PAIR")) : 1;
   for (int l = 0; l < NLAYER; ++l) {
     const Layer& L = ctx->layer[l];
-    if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, FPW, TM)) return 1;
-    if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, FPW, TM)) return 1;
+    if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, FPW)) return 1;
+    if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, FPW)) return 1;
   }
   const uint64_t cap_rows = (uint64_t)ctx->chunk * NSTREAM;
   for (int b = 0; b < 2; ++b) {
     // a plane holds cap_rows x FP floats; viewed with K = K0P it has room for more rows, but the same
     // row capacity is all a wave ever uses
-    if (make_map(enc, &s->act_hi[b][0], ctx->act[b].hi, K0P, cap_rows, TN)) return 1;
-    if (make_map(enc, &s->act_lo[b][0], ctx->act[b].lo, K0P, cap_rows, TN)) return 1;
-    if (make_map(enc, &s->act_hi[b][1], ctx->act[b].hi, FP, cap_rows, TN)) return 1;
-    if (make_map(enc, &s->act_lo[b][1], ctx->act[b].lo, FP, cap_rows, TN)) return 1;
+    if (make_map(enc, &s->act_hi[b][0], ctx->act[b].hi, K0P, cap_rows)) return 1;
+    if (make_map(enc, &s->act_lo[b][0], ctx->act[b].lo, K0P, cap_rows)) return 1;
+    if (make_map(enc, &s->act_hi[b][1], ctx->act[b].hi, FP, cap_rows)) return 1;
+    if (make_map(enc, &s->act_lo[b][1], ctx->act[b].lo, FP, cap_rows)) return 1;
   }
-  FPS_CUDA(cudaFuncSetAttribute(layer_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  FPS_CUDA(cudaFuncSetAttribute(layer_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  FPS_CUDA(cudaFuncSetAttribute(layer_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  FPS_CUDA(cudaFuncSetAttribute(layer_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  if (set_smem(layer_tc_kernel<4, false>) || set_smem(layer_tc_kernel<4, true>) ||
+      set_smem(layer_tc_kernel<1, false>) || set_smem(layer_tc_kernel<1, true>) ||
+      set_smem(layer_tc_pair_kernel<4, false>) || set_smem(layer_tc_pair_kernel<4, true>) ||
+      set_smem(layer_tc_pair_kernel<1, false>) || set_smem(layer_tc_pair_kernel<1, true>))
+    return 1;
   return 0;
 }
 
@@ -406,15 +507,37 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.rows = points * streams;
   P.nk = L.Kp / TK;
   P.row_tiles = (int)((P.rows + TN - 1) / TN);
-  const int total = P.row_tiles * N_FEAT_TILES;
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-#define FPS_TC_LAUNCH(S_, LAST_)                                                                              \
-  layer_tc_kernel<S_, LAST_><<<grid, TC_THREADS, TC_SMEM, st>>>(s->w_hi[l], s->w_lo[l], s->act_hi[b][kv],      \
-                                                                 s->act_lo[b][kv], P)
-  if (streams == 4) {
-    if (last) FPS_TC_LAUNCH(4, true); else FPS_TC_LAUNCH(4, false);
+  static const int dbg = getenv("FPS_TC_DEBUG") ? atoi(getenv("FPS_TC_DEBUG")) : 0;
+  P.debug = dbg;
+  static const int seg = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : SEG_SLABS;
+  P.seg = seg;
+  // Truncation-bias compensation (see header): the tensor core rounds the fp32 accumulator toward zero
+  // after every MMA, which shrinks a K_seg-long segment sum by kappa(K_seg) on average; measured on B200
+  // against the fp64 oracle (tools/calibrate_kappa.py): 4.2 ulp at K=32, 6 ulp at K=64, 9 ulp at K=128,
+  // i.e. kappa(K) = 4.2 * 2^-23 * (K/32)^0.55.  FPS_TC_KAPPA overrides (calibration runs).
+  auto kappa_of = [](int kseg) { return 4.2f * 1.1920929e-7f * powf((float)kseg / 32.f, 0.55f); };
+  static const char* kenv = getenv("FPS_TC_KAPPA");
+  const int tail = (P.nk % seg) ? (P.nk % seg) : seg;
+  P.gain = 1.0f + (kenv ? (float)atof(kenv) : kappa_of(seg * TK));
+  P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail * TK));
+  const int ncta = s->pair ? 2 : 1;
+  const int total = P.row_tiles * (N_FEAT_TILES / ncta);          // tiles of a CTA (pair)
+  const int groups_max = ctx->sm_count / ncta;
+  const int grid = (total < groups_max ? total : groups_max) * ncta;
+#define FPS_TC_LAUNCH(K_, S_, LAST_) \
+  K_<S_, LAST_><<<grid, TC_THREADS, TC_SMEM, st>>>(s->w_hi[l], s->w_lo[l], s->act_hi[b][kv], s->act_lo[b][kv], P)
+  if (s->pair) {
+    if (streams == 4) {
+      if (last) FPS_TC_LAUNCH(layer_tc_pair_kernel, 4, true); else FPS_TC_LAUNCH(layer_tc_pair_kernel, 4, false);
+    } else {
+      if (last) FPS_TC_LAUNCH(layer_tc_pair_kernel, 1, true); else FPS_TC_LAUNCH(layer_tc_pair_kernel, 1, false);
+    }
   } else {
-    if (last) FPS_TC_LAUNCH(1, true); else FPS_TC_LAUNCH(1, false);
+    if (streams == 4) {
+      if (last) FPS_TC_LAUNCH(layer_tc_kernel, 4, true); else FPS_TC_LAUNCH(layer_tc_kernel, 4, false);
+    } else {
+      if (last) FPS_TC_LAUNCH(layer_tc_kernel, 1, true); else FPS_TC_LAUNCH(layer_tc_kernel, 1, false);
+    }
   }
 #undef FPS_TC_LAUNCH
   count_launch();
