@@ -35,6 +35,7 @@ import numpy as np
 import torch
 
 from . import _lib, weights as _weights
+from .parallel import PackedNormal, allreduce_sum
 
 F, FP = _lib.F, _lib.FP
 _JITTER_LADDER = [0.0, 8.0, 128.0, 2048.0, 32768.0, 2.0 ** 20, 2.0 ** 26, 2.0 ** 32]  # x eps x max_diag
@@ -169,9 +170,7 @@ class Solver:
         return H, DH
 
     def _allreduce(self, t):
-        import torch.distributed as dist
-
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+        allreduce_sum(t, self.process_group)
 
     def _factor(self):
         """Assemble LHS per lambda and Cholesky-factor it (fps_assemble_factor), raising the diagonal
@@ -225,10 +224,9 @@ class Solver:
             else:
                 self._Hp, self._DHp = self._features(x64[0], x64[1], True)      # solver.py:162-166
                 self._Hbcp, _ = self._features(x64[2], x64[3], False)           # solver.py:173-175
-                pack = torch.zeros(2 * FP * FP + FP + 2, dtype=torch.float64, device=self._tdev)
-                self._G64 = pack[: FP * FP].view(FP, FP)
-                self._Gbc64 = pack[FP * FP: 2 * FP * FP].view(FP, FP)
-                self._s64 = pack[2 * FP * FP: 2 * FP * FP + FP]
+                packed = PackedNormal(self._tdev)
+                pack = packed.buf
+                self._G64, self._Gbc64, self._s64 = packed.G, packed.Gbc, packed.s
                 st = self._stream()
                 n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
                 if n_loc:
@@ -239,12 +237,10 @@ class Solver:
                                                         self._Gbc64.data_ptr(), st), "fps_gram_accum(bc)")
                     _lib.check(self._lib.fps_colsum_accum(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
                                                           self._s64.data_ptr(), st), "fps_colsum_accum")  # solver.py:176-178
-                pack[-2] = n_loc
-                pack[-1] = nbc_loc
+                packed.set_counts(n_loc, nbc_loc)
                 if self.distributed:
-                    self._allreduce(pack)  # the path's one exchange step
-                    counts = pack[-2:].cpu()
-                    self.NO, self.NdO = int(round(counts[0].item())), int(round(counts[1].item()))
+                    packed.allreduce(self.process_group)  # the path's one exchange step
+                    self.NO, self.NdO = packed.counts()
                 else:
                     self.NO, self.NdO = n_loc, nbc_loc
                 self._pack = pack
