@@ -326,6 +326,10 @@ def run_ours(args):
                    "kernels_ms": {k: round(v[0] / 3, 3) for k, v in pb.items() if v[1]}}
         del Fm
 
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----------------------------------------------------------
@@ -379,7 +383,7 @@ def run_ours(args):
     }
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----------------------------------------
     if world == 1 and not args.no_cpu:
-        n_sample = 256
+        n_sample = 512
         dt, threads = cpu_reference_step(n_sample)
         dt_fwd, _ = cpu_reference_step(10000, laplace="forward")
         out["cpu_baseline"] = {
@@ -388,7 +392,9 @@ def run_ours(args):
                       f"sweeps, fp32, precompute+solve) took {dt:.1f} s on {threads} threads of {os.cpu_count()} cores",
             "forward_mode_port_points_per_s": 10000 / dt_fwd,
         }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
