@@ -52,6 +52,11 @@ SIGNATURES = {
     "fps_solve_factored": (_i32, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "fps_reconstruct": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "fps_mse": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "fps_features_f64": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "fps_gram_accum_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fps_colsum_accum_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "fps_project_rhs_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "fps_reconstruct_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "fps_launch_count": (_i64, []),
     "fps_profile_enable": (_i32, [_vp, _i32]),
     "fps_profile_reset": (_i32, [_vp]),

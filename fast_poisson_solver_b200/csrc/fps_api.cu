@@ -61,6 +61,19 @@ void set_error(const char* fmt, ...) {
 }
 
 // Pad a (rows x cols) torch weight[out][in] to (FPW x Kp), split into TF32 hi/lo planes on the host.
+static int upload_layer_f64(fps_ctx* ctx, int l, const float* w, const float* b, int cols, int Kp) {
+  std::vector<double> w64((size_t)FP * Kp, 0.0), b64(FP, 0.0);
+  for (int r = 0; r < F; ++r) {
+    for (int c = 0; c < cols; ++c) w64[(size_t)r * Kp + c] = (double)w[(size_t)r * cols + c];
+    b64[r] = (double)b[r];
+  }
+  FPS_CUDA(cudaMalloc(&ctx->w64[l], w64.size() * sizeof(double)));
+  FPS_CUDA(cudaMalloc(&ctx->b64[l], b64.size() * sizeof(double)));
+  FPS_CUDA(cudaMemcpy(ctx->w64[l], w64.data(), w64.size() * sizeof(double), cudaMemcpyHostToDevice));
+  FPS_CUDA(cudaMemcpy(ctx->b64[l], b64.data(), b64.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 static int upload_layer(Layer& L, const float* w, const float* b, int cols, int Kp) {
   std::vector<float> hi((size_t)FPW * Kp, 0.f), lo((size_t)FPW * Kp, 0.f), bias(FPW, 0.f);
   for (int r = 0; r < F; ++r) {
@@ -119,6 +132,8 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 18944;
   int rc = upload_layer(ctx->layer[0], w->h_w0, w->h_b0, K0, K0P);
   for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer(ctx->layer[l + 1], w->h_wh[l], w->h_bh[l], F, FP);
+  if (rc == 0) rc = upload_layer_f64(ctx, 0, w->h_w0, w->h_b0, K0, K0P);
+  for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer_f64(ctx, l + 1, w->h_wh[l], w->h_bh[l], F, FP);
   if (rc) { fps_destroy(ctx); return rc; }
   double ffm[4 * NFREQ];
   for (int j = 0; j < NFREQ; ++j) {
@@ -131,8 +146,9 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   FPS_CUDA(cudaMemcpy(ctx->ffm, ffm, sizeof(ffm), cudaMemcpyHostToDevice));
   const size_t plane = (size_t)ctx->chunk * NSTREAM * FP * sizeof(float);
   for (int i = 0; i < 2; ++i) {
-    FPS_CUDA(cudaMalloc(&ctx->act[i].hi, plane));
-    FPS_CUDA(cudaMalloc(&ctx->act[i].lo, plane));
+    // hi and lo planes are one allocation: the fp64 engine views the pair as chunk*4*FP doubles
+    FPS_CUDA(cudaMalloc(&ctx->act[i].hi, 2 * plane));
+    ctx->act[i].lo = ctx->act[i].hi + plane / sizeof(float);
   }
   ctx->partial_bytes = (size_t)1024 * 64 * 64 * sizeof(double);  // 32 MiB of split-K tiles
   FPS_CUDA(cudaMalloc(&ctx->partial, ctx->partial_bytes));
@@ -150,11 +166,12 @@ int fps_destroy(fps_ctx* ctx) {
     cudaFree(ctx->layer[l].w_hi);
     cudaFree(ctx->layer[l].w_lo);
     cudaFree(ctx->layer[l].bias);
+    cudaFree(ctx->w64[l]);
+    cudaFree(ctx->b64[l]);
   }
   cudaFree(ctx->ffm);
   for (int i = 0; i < 2; ++i) {
     cudaFree(ctx->act[i].hi);
-    cudaFree(ctx->act[i].lo);
   }
   cudaFree(ctx->partial);
   delete ctx->prof;
@@ -254,6 +271,62 @@ int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const d
 int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream) {
   FPS_REQUIRE(ctx && pred && ref && loss64 && n > 0, "fps_mse: bad argument");
   return launch_mse(pred, ref, n, loss64, (cudaStream_t)stream);
+}
+
+// ---- fp64 engine entry points (precision = float64) ----------------------------------------------
+int fps_features_f64(fps_ctx* ctx, const double* x, const double* y, int64_t n, double* H, double* DH, int64_t ld,
+                     void* stream) {
+  FPS_REQUIRE(ctx && x && y && H, "fps_features_f64: null argument");
+  FPS_REQUIRE(ld >= FP && ld % 2 == 0, "fps_features_f64: ld=%lld must be >= %d and even", (long long)ld, FP);
+  FPS_REQUIRE((uintptr_t)H % 16 == 0 && (uintptr_t)DH % 16 == 0, "fps_features_f64: H/DH must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int streams = DH ? NSTREAM : 1;
+  const int64_t wave = (int64_t)ctx->chunk * (NSTREAM / streams);
+  for (int64_t p0 = 0; p0 < n; p0 += wave) {
+    const int64_t np = (n - p0 < wave) ? n - p0 : wave;
+    int cur = 0;
+    double* buf[2] = {reinterpret_cast<double*>(ctx->act[0].hi), reinterpret_cast<double*>(ctx->act[1].hi)};
+    {
+      ProfScope ps(ctx, FPS_PROF_FOURIER, st);
+      if (int rc = launch_fourier_f64(ctx, x + p0, y + p0, np, streams, buf[cur], st)) return rc;
+    }
+    for (int l = 0; l < NLAYER; ++l) {
+      const bool last = (l == NLAYER - 1);
+      ProfScope ps(ctx, l == 0 ? FPS_PROF_LAYER0 : (last ? FPS_PROF_LAST : FPS_PROF_HIDDEN), st);
+      if (int rc = launch_layer_f64(ctx, l, buf[cur], buf[cur ^ 1], np, streams, last, H + p0 * ld,
+                                    DH ? DH + p0 * ld : nullptr, ld, st))
+        return rc;
+      cur ^= 1;
+    }
+  }
+  return 0;
+}
+
+int fps_gram_accum_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, double* G64, void* stream) {
+  FPS_REQUIRE(ctx && A && G64 && ld >= FP, "fps_gram_accum_f64: bad argument");
+  ProfScope ps(ctx, FPS_PROF_GRAM, (cudaStream_t)stream);
+  return launch_atb_f64_d(ctx, A, ld, FP, A, ld, FP, n, G64, FP, true, (cudaStream_t)stream);
+}
+
+int fps_colsum_accum_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, double* s64, void* stream) {
+  FPS_REQUIRE(ctx && A && s64 && ld >= FP, "fps_colsum_accum_f64: bad argument");
+  return launch_colsum_d(A, n, ld, s64, (cudaStream_t)stream);
+}
+
+int fps_project_rhs_f64(fps_ctx* ctx, const double* DH, int64_t n, int64_t ld, const double* Fm, int64_t ldf, int B,
+                        double* R64, int64_t ldr, void* stream) {
+  FPS_REQUIRE(ctx && DH && Fm && R64, "fps_project_rhs_f64: null argument");
+  FPS_REQUIRE(ld >= FP && ldf >= B && ldr >= B, "fps_project_rhs_f64: bad leading dimension");
+  ProfScope ps(ctx, FPS_PROF_PROJECT, (cudaStream_t)stream);
+  return launch_atb_f64_d(ctx, DH, ld, FP, Fm, ldf, B, n, R64, ldr, false, (cudaStream_t)stream);
+}
+
+int fps_reconstruct_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
+                        const double* bias64, int B, double* out, int64_t ldo, void* stream) {
+  FPS_REQUIRE(ctx && A && W64 && out, "fps_reconstruct_f64: null argument");
+  FPS_REQUIRE(ldw >= B && ldo >= B, "fps_reconstruct_f64: bad leading dimension");
+  ProfScope ps(ctx, FPS_PROF_RECONSTRUCT, (cudaStream_t)stream);
+  return launch_reconstruct_d(ctx, A, n, ld, W64, ldw, bias64, B, out, ldo, (cudaStream_t)stream);
 }
 
 int64_t fps_launch_count(void) { return (int64_t)g_launches; }

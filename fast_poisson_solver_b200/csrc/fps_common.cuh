@@ -57,6 +57,8 @@ struct fps_ctx {
   size_t partial_bytes;
   size_t workspace_bytes;
   void* tc_state;         // engine-private (tensor maps), owned by layer_tc.cu
+  double* w64[fps::NLAYER]; // fp64 engine: (FP, Kp) row-major weights, zero padded
+  double* b64[fps::NLAYER]; // fp64 engine: (FP) biases
 };
 
 namespace fps {
@@ -132,4 +134,17 @@ __device__ __forceinline__ void split_store(float* hi, float* lo, float v) {
   *lo = v - h;
 }
 
+}  // namespace fps
+
+namespace fps {
+// ---- fp64 engine (precision = float64) --------------------------------------------------------
+int launch_fourier_f64(const fps_ctx* ctx, const double* x, const double* y, int64_t n, int streams, double* out,
+                       cudaStream_t st);
+int launch_layer_f64(const fps_ctx* ctx, int l, const double* in, double* out, int64_t points, int streams, bool last,
+                     double* H, double* DH, int64_t ld, cudaStream_t st);
+int launch_atb_f64_d(const fps_ctx* ctx, const double* A, int64_t lda, int M, const double* B, int64_t ldb, int Ncols,
+                     int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st);
+int launch_colsum_d(const double* A, int64_t n, int64_t ld, double* s64, cudaStream_t st);
+int launch_reconstruct_d(const fps_ctx* ctx, const double* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
+                         const double* bias, int B, double* out, int64_t ldo, cudaStream_t st);
 }  // namespace fps

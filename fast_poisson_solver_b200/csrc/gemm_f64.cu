@@ -1,4 +1,4 @@
-// FP64-accumulated contractions over fp32 feature matrices (DMMA m8n8k4 tensor path).
+// FP64-accumulated contractions over the feature matrices (DMMA m8n8k4 tensor path).
 //
 //   atb      C(M x Nc) += A^T B   over n rows      Gram  DH^T DH        solver.py:167
 //                                                  BC    H_bc^T H_bc    solver.py:196
@@ -6,9 +6,10 @@
 //   nn       out(n x B) = A W + bias               u = H w + b, f = DH w, u_bc = H_bc w + b
 //                                                                        solver.py:327-330
 // Why fp64: the normal matrix has cond ~1e15; accumulating the Gram or the RHS
-// projection at fp32 grade moves u by 1e-4..3e-2, far beyond the 1e-5 parity bar.  Inputs stay
-// fp32 in HBM (that is what the feature kernel produces) and are widened on the way into shared
-// memory, so HBM traffic is the fp32 footprint.
+// projection at fp32 grade moves u by 1e-4..3e-2, far beyond the 1e-5 parity bar.  In the default
+// (precision=float32) mode the inputs stay fp32 in HBM (that is what the feature kernel produces) and
+// are widened on the way into shared memory, so HBM traffic is the fp32 footprint; in
+// precision=float64 mode the same kernels read fp64 features (template parameter).
 //
 // Split-K (over rows) partial tiles are written to a workspace and summed in a fixed order by a
 // second kernel, so results are bit-reproducible for a given (n, chunking) - no fp64 atomics.
@@ -28,62 +29,86 @@ constexpr int GK = 32;         // rows (contraction) per step
 constexpr int GS = GT + 4;     // smem row stride in doubles: == 4 (mod 16) -> conflict-free fragment loads
 constexpr int GTHREADS = 128;  // 4 warps, each a 32x32 sub-tile
 
-// Load a (GK x GT) fp32 tile whose rows are contraction indices: element (r, c) = P[(k0+r)*ld + c0+c],
-// zero outside [kend) x [ncols).  16 floats per thread as 4 float4 (scalar fallback when unaligned).
+// Four consecutive elements of a row, widened to double; zero outside [ncols).
+template <typename T>
+__device__ __forceinline__ void load4(const T* __restrict__ p, int c, int ncols, bool vec_ok, double* o);
+
+template <>
+__device__ __forceinline__ void load4<float>(const float* __restrict__ p, int c, int ncols, bool vec_ok, double* o) {
+  if (vec_ok && c + 3 < ncols) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = (c + e < ncols) ? (double)__ldg(p + e) : 0.0;
+  }
+}
+template <>
+__device__ __forceinline__ void load4<double>(const double* __restrict__ p, int c, int ncols, bool vec_ok, double* o) {
+  if (vec_ok && c + 3 < ncols) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = (c + e < ncols) ? __ldg(p + e) : 0.0;
+  }
+}
+
+// Register image of a (GK x GT) tile whose rows are contraction indices: 16 elements per thread.
+// fp32 inputs are kept as fp32 in registers (half the footprint) and widened when stored to smem.
+template <typename T>
 struct TileRegs {
-  float4 v[4];
+  T v[16];
 };
 
-__device__ __forceinline__ void load_tile_kn(TileRegs& R, const float* __restrict__ P, int64_t ld, int64_t k0,
+template <typename T>
+__device__ __forceinline__ void load_tile_kn(TileRegs<T>& R, const T* __restrict__ P, int64_t ld, int64_t k0,
                                              int64_t kend, int c0, int ncols, bool vec_ok) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int idx = q * GTHREADS + threadIdx.x;
     const int r = idx / 16, c = (idx % 16) * 4;
-    float4 v = make_float4(0, 0, 0, 0);
+    double o[4] = {0.0, 0.0, 0.0, 0.0};
     const int64_t k = k0 + r;
-    if (k < kend) {
-      const float* p = P + k * ld + c0 + c;
-      if (vec_ok && c0 + c + 3 < ncols) {
-        v = __ldg(reinterpret_cast<const float4*>(p));
-      } else {
-        if (c0 + c + 0 < ncols) v.x = __ldg(p + 0);
-        if (c0 + c + 1 < ncols) v.y = __ldg(p + 1);
-        if (c0 + c + 2 < ncols) v.z = __ldg(p + 2);
-        if (c0 + c + 3 < ncols) v.w = __ldg(p + 3);
-      }
-    }
-    R.v[q] = v;
+    if (k < kend) load4<T>(P + k * ld + c0 + c, c0 + c, ncols, vec_ok, o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) R.v[q * 4 + e] = (T)o[e];
   }
 }
 
-__device__ __forceinline__ void store_tile_kn(const TileRegs& R, double* S) {
+template <typename T>
+__device__ __forceinline__ void store_tile_kn(const TileRegs<T>& R, double* S) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int idx = q * GTHREADS + threadIdx.x;
     const int r = idx / 16, c = (idx % 16) * 4;
     double2* d = reinterpret_cast<double2*>(S + r * GS + c);
-    d[0] = make_double2((double)R.v[q].x, (double)R.v[q].y);
-    d[1] = make_double2((double)R.v[q].z, (double)R.v[q].w);
+    d[0] = make_double2((double)R.v[q * 4 + 0], (double)R.v[q * 4 + 1]);
+    d[1] = make_double2((double)R.v[q * 4 + 2], (double)R.v[q * 4 + 3]);
   }
+}
+
+__device__ __forceinline__ void tri_tile(int t, int& ti, int& tj) {  // t enumerates the lower triangle, ti >= tj
+  ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  while (ti * (ti + 1) / 2 > t) --ti;
+  tj = t - ti * (ti + 1) / 2;
 }
 
 // ------------------------------------------------------------------------------------------------
 // C_partial[slice][tile] = A^T B over this slice's rows
 // ------------------------------------------------------------------------------------------------
+template <typename TA, typename TB>
 __global__ void __launch_bounds__(GTHREADS)
-atb_f64_kernel(const float* __restrict__ A, int64_t lda, int M, const float* __restrict__ B, int64_t ldb, int Nc,
+atb_f64_kernel(const TA* __restrict__ A, int64_t lda, int M, const TB* __restrict__ B, int64_t ldb, int Nc,
                int64_t n, int64_t rows_per_slice, int tiles_j, int symmetric, double* __restrict__ partial,
                int vecA, int vecB) {
   __shared__ __align__(16) double As[GK * GS];
   __shared__ __align__(16) double Bs[GK * GS];
   int ti, tj;
-  if (symmetric) {  // blockIdx.x enumerates the lower triangle: ti >= tj
-    int t = blockIdx.x;
-    ti = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    tj = t - ti * (ti + 1) / 2;
+  if (symmetric) {
+    tri_tile(blockIdx.x, ti, tj);
   } else {
     ti = blockIdx.x / tiles_j;
     tj = blockIdx.x % tiles_j;
@@ -100,17 +125,18 @@ atb_f64_kernel(const float* __restrict__ A, int64_t lda, int M, const float* __r
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
 
-  TileRegs ra, rb;
-  load_tile_kn(ra, A, lda, kbeg, kend, ti * GT, M, vecA);
-  load_tile_kn(rb, B, ldb, kbeg, kend, tj * GT, Nc, vecB);
+  TileRegs<TA> ra;
+  TileRegs<TB> rb;
+  load_tile_kn<TA>(ra, A, lda, kbeg, kend, ti * GT, M, vecA);
+  load_tile_kn<TB>(rb, B, ldb, kbeg, kend, tj * GT, Nc, vecB);
   for (int64_t k0 = kbeg; k0 < kend; k0 += GK) {
     __syncthreads();
-    store_tile_kn(ra, As);
-    store_tile_kn(rb, Bs);
+    store_tile_kn<TA>(ra, As);
+    store_tile_kn<TB>(rb, Bs);
     __syncthreads();
     if (k0 + GK < kend) {
-      load_tile_kn(ra, A, lda, k0 + GK, kend, ti * GT, M, vecA);
-      load_tile_kn(rb, B, ldb, k0 + GK, kend, tj * GT, Nc, vecB);
+      load_tile_kn<TA>(ra, A, lda, k0 + GK, kend, ti * GT, M, vecA);
+      load_tile_kn<TB>(rb, B, ldb, k0 + GK, kend, tj * GT, Nc, vecB);
     }
 #pragma unroll
     for (int kk = 0; kk < GK / 4; ++kk) {
@@ -141,10 +167,7 @@ __global__ void atb_reduce_kernel(const double* __restrict__ partial, int ntiles
   const int tile = blockIdx.x;
   int ti, tj;
   if (symmetric) {
-    ti = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-    while (ti * (ti + 1) / 2 > tile) --ti;
-    tj = tile - ti * (ti + 1) / 2;
+    tri_tile(tile, ti, tj);
   } else {
     ti = tile / tiles_j;
     tj = tile % tiles_j;
@@ -166,9 +189,9 @@ __global__ void atb_reduce_kernel(const double* __restrict__ partial, int ntiles
 
 // Few right-hand sides (B <= 8): R(FP x B) += DH^T F is a streaming GEMV bounded by the HBM read of DH.
 // Each thread owns up to 3 feature columns (t, t+256, t+512) and B fp64 accumulators per column.
-template <int NB>
+template <int NB, typename TA, typename TB>
 __global__ void __launch_bounds__(256)
-atb_small_kernel(const float* __restrict__ A, int64_t lda, int M, const float* __restrict__ B, int64_t ldb,
+atb_small_kernel(const TA* __restrict__ A, int64_t lda, int M, const TB* __restrict__ B, int64_t ldb,
                  int nb, int64_t n, int64_t rows_per_cta, double* __restrict__ partial) {
   const int t = threadIdx.x;
   double acc[3][NB];
@@ -180,16 +203,17 @@ atb_small_kernel(const float* __restrict__ A, int64_t lda, int M, const float* _
   const int64_t kend = min(n, kbeg + rows_per_cta);
   const bool has2 = t + 512 < M;
   for (int64_t k = kbeg; k < kend; k += 4) {
-    float a[4][3], f[4][NB];
+    TA a[4][3];
+    TB f[4][NB];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const bool ok = k + u < kend;
-      const float* row = A + (k + u) * lda;
-      a[u][0] = ok ? __ldg(row + t) : 0.f;
-      a[u][1] = ok ? __ldg(row + t + 256) : 0.f;
-      a[u][2] = (ok && has2) ? __ldg(row + t + 512) : 0.f;
+      const TA* row = A + (k + u) * lda;
+      a[u][0] = ok ? __ldg(row + t) : (TA)0;
+      a[u][1] = ok ? __ldg(row + t + 256) : (TA)0;
+      a[u][2] = (ok && has2) ? __ldg(row + t + 512) : (TA)0;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) f[u][j] = (ok && j < nb) ? __ldg(B + (k + u) * ldb + j) : 0.f;
+      for (int j = 0; j < NB; ++j) f[u][j] = (ok && j < nb) ? __ldg(B + (k + u) * ldb + j) : (TB)0;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -217,8 +241,9 @@ __global__ void atb_small_reduce_kernel(const double* __restrict__ partial, int 
   C[(int64_t)r * ldc + j] += s;
 }
 
-int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const float* B, int64_t ldb, int Nc,
-                   int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st) {
+template <typename TA, typename TB>
+int launch_atb_t(const fps_ctx* ctx, const TA* A, int64_t lda, int M, const TB* B, int64_t ldb, int Nc, int64_t n,
+                 double* C, int64_t ldc, bool symmetric, cudaStream_t st) {
   if (n <= 0 || M <= 0 || Nc <= 0) return 0;
   FPS_REQUIRE(M <= FP, "atb: M=%d exceeds %d", M, FP);
   if (!symmetric && Nc <= 8) {
@@ -226,10 +251,10 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
     ctas = std::min<int64_t>(ctas, (int64_t)(ctx->partial_bytes / (768 * 8 * sizeof(double))));
     const int64_t rpc = ((n + ctas - 1) / ctas + 3) / 4 * 4;
     ctas = (n + rpc - 1) / rpc;
-    // columns t+256 always < 704 <= lda; t+512 guarded by has2
+    // columns t and t+256 are always < 704 <= lda; t+512 is guarded by has2
     FPS_REQUIRE(M > 512 && lda >= M, "atb small path expects the padded feature matrix");
-#define FPS_SMALL(NB_)                                                                                        \
-  atb_small_kernel<NB_><<<(unsigned)ctas, 256, 0, st>>>(A, lda, M, B, ldb, Nc, n, rpc, ctx->partial);            \
+#define FPS_SMALL(NB_)                                                                                         \
+  atb_small_kernel<NB_, TA, TB><<<(unsigned)ctas, 256, 0, st>>>(A, lda, M, B, ldb, Nc, n, rpc, ctx->partial);   \
   atb_small_reduce_kernel<NB_><<<(M * NB_ + 255) / 256, 256, 0, st>>>(ctx->partial, (int)ctas, M, Nc, C, ldc)
     if (Nc == 1) { FPS_SMALL(1); }
     else if (Nc == 2) { FPS_SMALL(2); }
@@ -254,8 +279,8 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
   const int vecA = (lda % 4 == 0) && ((uintptr_t)A % 16 == 0);
   const int vecB = (ldb % 4 == 0) && ((uintptr_t)B % 16 == 0);
   dim3 grid((unsigned)ntiles, (unsigned)slices);
-  atb_f64_kernel<<<grid, GTHREADS, 0, st>>>(A, lda, M, B, ldb, Nc, n, rps, tiles_j, symmetric ? 1 : 0, ctx->partial,
-                                            vecA, vecB);
+  atb_f64_kernel<TA, TB><<<grid, GTHREADS, 0, st>>>(A, lda, M, B, ldb, Nc, n, rps, tiles_j, symmetric ? 1 : 0,
+                                                    ctx->partial, vecA, vecB);
   FPS_CUDA(cudaGetLastError());
   atb_reduce_kernel<<<ntiles, 256, 0, st>>>(ctx->partial, ntiles, (int)slices, tiles_j, symmetric ? 1 : 0, M, Nc, C,
                                             ldc);
@@ -264,10 +289,20 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
   return 0;
 }
 
+int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const float* B, int64_t ldb, int Ncols,
+                   int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st) {
+  return launch_atb_t<float, float>(ctx, A, lda, M, B, ldb, Ncols, n, C, ldc, symmetric, st);
+}
+int launch_atb_f64_d(const fps_ctx* ctx, const double* A, int64_t lda, int M, const double* B, int64_t ldb, int Ncols,
+                     int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st) {
+  return launch_atb_t<double, double>(ctx, A, lda, M, B, ldb, Ncols, n, C, ldc, symmetric, st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Column sums in fp64 (H_bc^T 1, solver.py:176-178).  N_bc is small (4G+4); one CTA per 64 columns.
 // ------------------------------------------------------------------------------------------------
-__global__ void colsum_kernel(const float* __restrict__ A, int64_t n, int64_t ld, double* __restrict__ s64) {
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ A, int64_t n, int64_t ld, double* __restrict__ s64) {
   __shared__ double red[4][64];
   const int c = blockIdx.x * 64 + threadIdx.x % 64;
   const int g = threadIdx.x / 64;
@@ -280,21 +315,29 @@ __global__ void colsum_kernel(const float* __restrict__ A, int64_t n, int64_t ld
 
 int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st) {
   if (n <= 0) return 0;
-  colsum_kernel<<<FP / 64, 256, 0, st>>>(A, n, ld, s64);
+  colsum_kernel<float><<<FP / 64, 256, 0, st>>>(A, n, ld, s64);
+  count_launch();
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_colsum_d(const double* A, int64_t n, int64_t ld, double* s64, cudaStream_t st) {
+  if (n <= 0) return 0;
+  colsum_kernel<double><<<FP / 64, 256, 0, st>>>(A, n, ld, s64);
   count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// out(n x B) = A(n x FP) W(FP x B) + bias, fp64 accumulation, fp32 in / fp32 out.
+// out(n x B) = A(n x FP) W(FP x B) + bias, fp64 accumulation.
 // Tile 64 rows x 64 columns, K steps of 32; A fragment loads want a row stride == 4 (mod 16).
 // ------------------------------------------------------------------------------------------------
 constexpr int NS_A = GK + 4;  // 36
 
+template <typename TA, typename TO>
 __global__ void __launch_bounds__(GTHREADS)
-nn_f64_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
-              const double* __restrict__ bias, int B, float* __restrict__ out, int64_t ldo) {
+nn_f64_kernel(const TA* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
+              const double* __restrict__ bias, int B, TO* __restrict__ out, int64_t ldo) {
   __shared__ __align__(16) double As[GT * NS_A];
   __shared__ __align__(16) double Ws[GK * GS];
   const int64_t r0 = (int64_t)blockIdx.x * GT;
@@ -310,16 +353,16 @@ nn_f64_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double* 
 
   for (int k0 = 0; k0 < FP; k0 += GK) {
     __syncthreads();
-    // A tile: 64 rows x 32 k, 512 float4, 4 per thread
+    // A tile: 64 rows x 32 k, 512 groups of 4, 4 per thread
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int idx = q * GTHREADS + threadIdx.x;
       const int r = idx / 8, kq = (idx % 8) * 4;
-      float4 v = make_float4(0, 0, 0, 0);
-      if (r0 + r < n) v = __ldg(reinterpret_cast<const float4*>(A + (r0 + r) * ld + k0 + kq));
+      double o[4] = {0.0, 0.0, 0.0, 0.0};
+      if (r0 + r < n) load4<TA>(A + (r0 + r) * ld + k0 + kq, 0, 4, true, o);
       double2* d = reinterpret_cast<double2*>(As + r * NS_A + kq);
-      d[0] = make_double2((double)v.x, (double)v.y);
-      d[1] = make_double2((double)v.z, (double)v.w);
+      d[0] = make_double2(o[0], o[1]);
+      d[1] = make_double2(o[2], o[3]);
     }
     // W tile: 32 k x 64 columns of doubles, 2048 doubles, 16 per thread
 #pragma unroll
@@ -351,16 +394,16 @@ nn_f64_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double* 
       if (r < n) {
 #pragma unroll
         for (int e = 0; e < 2; ++e)
-          if (cc + e < B) out[r * ldo + cc + e] = (float)(c[i][j][e] + (bias ? bias[cc + e] : 0.0));
+          if (cc + e < B) out[r * ldo + cc + e] = (TO)(c[i][j][e] + (bias ? bias[cc + e] : 0.0));
       }
     }
 }
 
 // Few right-hand sides: one warp per row, W columns staged in shared memory; HBM-bound on A.
-template <int NB>
+template <int NB, typename TA, typename TO>
 __global__ void __launch_bounds__(256)
-nn_small_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
-                const double* __restrict__ bias, int B, float* __restrict__ out, int64_t ldo) {
+nn_small_kernel(const TA* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
+                const double* __restrict__ bias, int B, TO* __restrict__ out, int64_t ldo) {
   __shared__ double Ws[FP * NB];
   for (int e = threadIdx.x; e < FP * NB; e += blockDim.x) {
     const int k = e / NB, j = e % NB;
@@ -370,15 +413,16 @@ nn_small_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
   for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < n; r += nwarps) {
-    const float4* row = reinterpret_cast<const float4*>(A + r * ld);
+    const TA* row = A + r * ld;
     double acc[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) acc[j] = 0.0;
-    float4 v[6];
+    double v[6][4];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {  // 176 float4 per row: 5 full rounds of 32 lanes + 16
+    for (int q = 0; q < 6; ++q) {  // 176 groups of 4 per row: 5 full rounds of 32 lanes + 16
       const int i4 = q * 32 + lane;
-      v[q] = (i4 < FP / 4) ? __ldg(row + i4) : make_float4(0, 0, 0, 0);
+      v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+      if (i4 < FP / 4) load4<TA>(row + i4 * 4, 0, 4, true, v[q]);
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
@@ -387,10 +431,10 @@ nn_small_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double
         const double* w = Ws + (size_t)i4 * 4 * NB;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          acc[j] = fma((double)v[q].x, w[0 * NB + j], acc[j]);
-          acc[j] = fma((double)v[q].y, w[1 * NB + j], acc[j]);
-          acc[j] = fma((double)v[q].z, w[2 * NB + j], acc[j]);
-          acc[j] = fma((double)v[q].w, w[3 * NB + j], acc[j]);
+          acc[j] = fma(v[q][0], w[0 * NB + j], acc[j]);
+          acc[j] = fma(v[q][1], w[1 * NB + j], acc[j]);
+          acc[j] = fma(v[q][2], w[2 * NB + j], acc[j]);
+          acc[j] = fma(v[q][3], w[3 * NB + j], acc[j]);
         }
       }
     }
@@ -402,27 +446,38 @@ nn_small_kernel(const float* __restrict__ A, int64_t n, int64_t ld, const double
     if (lane == 0) {
 #pragma unroll
       for (int j = 0; j < NB; ++j)
-        if (j < B) out[r * ldo + j] = (float)(acc[j] + (bias ? bias[j] : 0.0));
+        if (j < B) out[r * ldo + j] = (TO)(acc[j] + (bias ? bias[j] : 0.0));
     }
   }
 }
 
-int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
-                       const double* bias, int B, float* out, int64_t ldo, cudaStream_t st) {
+template <typename TA, typename TO>
+int launch_reconstruct_t(const fps_ctx* ctx, const TA* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
+                         const double* bias, int B, TO* out, int64_t ldo, cudaStream_t st) {
   if (n <= 0 || B <= 0) return 0;
-  FPS_REQUIRE(ld % 4 == 0 && (uintptr_t)A % 16 == 0 && ld >= FP, "reconstruct: A must be 16-byte aligned, ld %% 4 == 0, ld >= %d", FP);
+  FPS_REQUIRE(ld % 4 == 0 && (uintptr_t)A % 16 == 0 && ld >= FP,
+              "reconstruct: A must be 16-byte aligned, ld %% 4 == 0, ld >= %d", FP);
   if (B <= 4) {
     const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
-    if (B == 1) nn_small_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
-    else if (B == 2) nn_small_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
-    else nn_small_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    if (B == 1) nn_small_kernel<1, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    else if (B == 2) nn_small_kernel<2, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    else nn_small_kernel<4, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
   } else {
     dim3 grid((unsigned)((n + GT - 1) / GT), (unsigned)((B + GT - 1) / GT));
-    nn_f64_kernel<<<grid, GTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    nn_f64_kernel<TA, TO><<<grid, GTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
   }
   count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
+                       const double* bias, int B, float* out, int64_t ldo, cudaStream_t st) {
+  return launch_reconstruct_t<float, float>(ctx, A, n, ld, W, ldw, bias, B, out, ldo, st);
+}
+int launch_reconstruct_d(const fps_ctx* ctx, const double* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
+                         const double* bias, int B, double* out, int64_t ldo, cudaStream_t st) {
+  return launch_reconstruct_t<double, double>(ctx, A, n, ld, W, ldw, bias, B, out, ldo, st);
 }
 
 // mean((pred - ref)^2) in fp64, single CTA (used only by the multi-lambda sweep, solver.py:312-314).

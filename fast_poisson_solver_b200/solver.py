@@ -18,8 +18,9 @@ Deliberate deviations from the reference:
   * ``solve`` also accepts ``f`` of shape (N, B) with ``bc`` of shape (N_bc, B) (or (B,) constants)
     and returns (N+N_bc, B) / (N, B) / (N_bc, B) tensors - the reference is single-RHS only.
   * ``runtime`` is measured with a stream synchronise on both sides.
-  * Features are evaluated at fp32 grade (3xTF32 tensor-core contractions, fp64 Fourier phases);
-    Gram matrix, RHS projection, factorisation and reconstruction accumulate in fp64.
+  * precision=torch.float32: features are evaluated at fp32 grade (3xTF32 tensor-core contractions,
+    fp64 Fourier phases); Gram matrix, RHS projection, factorisation and reconstruction accumulate in
+    fp64.  precision=torch.float64: everything, including the feature network, runs in fp64 (DMMA).
   * ``distributed=True``: every rank passes ITS shard of the collocation / boundary points and of
     the rows of ``f``; one all-reduce of the packed [Gram | BC Gram | column sums | counts] buffer
     in precompute and one of the projected right-hand sides per solve.
@@ -141,6 +142,12 @@ class Solver:
             _lib.check(self._lib.fps_create(C.byref(self._ctx), self._dev_index, C.byref(self._host_weights.struct),
                                             int(chunk_points), self.engine), "fps_create")
         self._ready = False
+        # precision=float64 runs the full-fp64 feature engine (DMMA) and keeps H / DH / outputs in fp64;
+        # precision=float32 runs the 3xTF32 tcgen05 engine with fp32 features and fp64 normal equations.
+        self._fdtype = torch.float64 if precision == torch.float64 else torch.float32
+
+    def _fn(self, name):
+        return getattr(self._lib, name + ("_f64" if self._fdtype == torch.float64 else ""))
 
     # ------------------------------------------------------------------------------------------
     def __del__(self):
@@ -161,10 +168,10 @@ class Solver:
     # ---- kernels ---------------------------------------------------------------------------------
     def _features(self, x64, y64, want_laplace):
         n = x64.numel()
-        H = torch.empty((n, FP), dtype=torch.float32, device=self._tdev)
-        DH = torch.empty((n, FP), dtype=torch.float32, device=self._tdev) if want_laplace else None
+        H = torch.empty((n, FP), dtype=self._fdtype, device=self._tdev)
+        DH = torch.empty((n, FP), dtype=self._fdtype, device=self._tdev) if want_laplace else None
         if n:
-            _lib.check(self._lib.fps_features(self._ctx, x64.data_ptr(), y64.data_ptr(), n, H.data_ptr(),
+            _lib.check(self._fn("fps_features")(self._ctx, x64.data_ptr(), y64.data_ptr(), n, H.data_ptr(),
                                               DH.data_ptr() if want_laplace else None, FP, self._stream()),
                        "fps_features")
         return H, DH
@@ -230,12 +237,12 @@ class Solver:
                 st = self._stream()
                 n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
                 if n_loc:
-                    _lib.check(self._lib.fps_gram_accum(self._ctx, self._DHp.data_ptr(), n_loc, FP,
+                    _lib.check(self._fn("fps_gram_accum")(self._ctx, self._DHp.data_ptr(), n_loc, FP,
                                                         self._G64.data_ptr(), st), "fps_gram_accum")  # solver.py:167
                 if nbc_loc:
-                    _lib.check(self._lib.fps_gram_accum(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
+                    _lib.check(self._fn("fps_gram_accum")(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
                                                         self._Gbc64.data_ptr(), st), "fps_gram_accum(bc)")
-                    _lib.check(self._lib.fps_colsum_accum(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
+                    _lib.check(self._fn("fps_colsum_accum")(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
                                                           self._s64.data_ptr(), st), "fps_colsum_accum")  # solver.py:176-178
                 packed.set_counts(n_loc, nbc_loc)
                 if self.distributed:
@@ -263,9 +270,6 @@ class Solver:
         self.Ht_bc = self.H_bc.t()
         self.DHtDH = self._G64[:F, :F].to(self.precision)
         self.Ht_bc_ones = self._s64[:F].to(self.precision).reshape(1, F)
-        if self.precision != torch.float32:
-            self.H, self.DH, self.H_bc = self.H.to(self.precision), self.DH.to(self.precision), self.H_bc.to(self.precision)
-            self.Dht, self.Ht_bc = self.DH.t(), self.H_bc.t()
 
     @property
     def LHSs(self):
@@ -336,7 +340,7 @@ class Solver:
             bt = bt.reshape(1, B).expand(nbc_loc, B)
         else:
             raise ValueError(f"bc has shape {tuple(bt.shape)}; expected ({nbc_loc}, {B}) or {B} constants")
-        return ft.to(torch.float32).contiguous(), bt, B
+        return ft.to(self._fdtype).contiguous(), bt, B
 
     def solve(self, f, bc):
         if not self._ready:
@@ -351,14 +355,14 @@ class Solver:
 
             R = torch.zeros((FP, B), dtype=torch.float64, device=self._tdev)
             if n_loc:
-                _lib.check(self._lib.fps_project_rhs(self._ctx, self._DHp.data_ptr(), n_loc, FP, F32.data_ptr(),
+                _lib.check(self._fn("fps_project_rhs")(self._ctx, self._DHp.data_ptr(), n_loc, FP, F32.data_ptr(),
                                                      F32.stride(0), B, R.data_ptr(), B, st), "fps_project_rhs")  # :301
             sum_bc = BC.to(torch.float64).sum(dim=0).contiguous()                                               # :302
             if self.distributed:
                 self._allreduce(R)
                 self._allreduce(sum_bc)
-            U = torch.empty((n_loc + nbc_loc, B), dtype=torch.float32, device=self._tdev)
-            Fp = torch.empty((n_loc, B), dtype=torch.float32, device=self._tdev)
+            U = torch.empty((n_loc + nbc_loc, B), dtype=self._fdtype, device=self._tdev)
+            Fp = torch.empty((n_loc, B), dtype=self._fdtype, device=self._tdev)
             W = torch.empty((FP, B), dtype=torch.float64, device=self._tdev)
             bias = torch.empty(B, dtype=torch.float64, device=self._tdev)
             best = None
@@ -415,10 +419,10 @@ class Solver:
         n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
         lib, ctx = self._lib, self._ctx
         if n_loc:
-            _lib.check(lib.fps_reconstruct(ctx, self._Hp.data_ptr(), n_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
+            _lib.check(self._fn("fps_reconstruct")(ctx, self._Hp.data_ptr(), n_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
                                            U.data_ptr(), B, st), "fps_reconstruct(u_pde)")
-            _lib.check(lib.fps_reconstruct(ctx, self._DHp.data_ptr(), n_loc, FP, W.data_ptr(), B, None, B,
+            _lib.check(self._fn("fps_reconstruct")(ctx, self._DHp.data_ptr(), n_loc, FP, W.data_ptr(), B, None, B,
                                            Fp.data_ptr(), B, st), "fps_reconstruct(f)")
         if nbc_loc:
-            _lib.check(lib.fps_reconstruct(ctx, self._Hbcp.data_ptr(), nbc_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
+            _lib.check(self._fn("fps_reconstruct")(ctx, self._Hbcp.data_ptr(), nbc_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
                                            U[n_loc:].data_ptr(), B, st), "fps_reconstruct(u_bc)")

@@ -113,6 +113,18 @@ int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const d
 /* Multi-lambda loss of solver.py:312-314 for one lambda: loss64[0] = mean((pred-ref)^2).        */
 int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream);
 
+/* ---- precision = torch.float64 (tests/test_solverclass.py:65-68 in the reference) ---------------
+ * Same contracts as the fp32 entry points above with every feature matrix, right-hand side and
+ * output in float64; features are evaluated entirely in fp64 on the DMMA tensor path.             */
+int fps_features_f64(fps_ctx* ctx, const double* x, const double* y, int64_t n,
+                     double* H, double* DH, int64_t ld, void* stream);
+int fps_gram_accum_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, double* G64, void* stream);
+int fps_colsum_accum_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, double* s64, void* stream);
+int fps_project_rhs_f64(fps_ctx* ctx, const double* DH, int64_t n, int64_t ld, const double* F, int64_t ldf,
+                        int B, double* R64, int64_t ldr, void* stream);
+int fps_reconstruct_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
+                        const double* bias64, int B, double* out, int64_t ldo, void* stream);
+
 /* ---- instrumentation (bench.py / profiles) ----------------------------------------------------
  * fps_launch_count: number of kernels this library has launched in this process (all contexts).
  * fps_profile_enable(ctx, 1): bracket every kernel launch of ctx with CUDA events on its stream.

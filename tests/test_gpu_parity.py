@@ -282,3 +282,49 @@ def test_save_load_roundtrip(solver_factory):
     os.remove(s.precompute_file)
     s2.precompute(xp, yp, xb, yb, name="rt_case", load=True)  # missing file -> silently recompute
     assert torch.equal(s2.solve(f, np.zeros(xb.size))[0], u0)
+
+
+# ---- precision = torch.float64: full-fp64 engine, no fp32 floor ---------------------------------
+def test_f64_features_vs_reference_golden(golden, solver_factory):
+    g = golden("features_seed0.npz")
+    s = solver_factory(precision=torch.float64)
+    H, DH = s._features(torch.tensor(g["x"], device="cuda"), torch.tensor(g["y"], device="cuda"), True)
+    Hb, _ = s._features(torch.tensor(g["x"], device="cuda"), torch.tensor(g["y"], device="cuda"), False)
+    assert H.dtype == torch.float64 and torch.all(H[:, 700:] == 0) and torch.all(DH[:, 700:] == 0)
+    assert o.rel_l2(H[:, :700].cpu().numpy(), g["H_f64"]) < 1e-13
+    assert o.rel_l2(DH[:, :700].cpu().numpy(), g["DH_f64"]) < 1e-13
+    assert o.rel_l2(Hb[:, :700].cpu().numpy(), g["H_f64"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["solve_G32_seed0.npz", "solve_G100_seed0.npz"])
+def test_f64_solver_vs_reference_golden(golden, solver_factory, name):
+    g = golden(name)
+    xp, yp, xb, yb = o.grid_problem(int(g["G"]))
+    s = solver_factory(precision=torch.float64)
+    s.precompute(xp, yp, xb, yb)
+    u, u_pde, u_bc, f_pred, rt = s.solve(g["f"], g["bc"])
+    assert u.dtype == torch.float64 and s.H.dtype == torch.float64 and s.precision == torch.float64
+    e_u = o.rel_l2(u.cpu().numpy(), g["u_f64"])
+    print(f"\n[{name} fp64 engine] u rel-L2 vs reference fp64 = {e_u:.3e}; jitter {s.jitter}")
+    assert e_u < 1e-6      # reproducibility of the reference's own fp64 LU on this cond~1e15 system
+    assert o.rel_l2(s.DHtDH.cpu().numpy()[::7, ::7], g["DHtDH_s7_f64"]) < 1e-12
+    assert o.rel_l2(f_pred.cpu().numpy(), g["f_pred_f64"]) < 1e-5
+
+
+def test_f64_rough_sources_meet_1e5_end_to_end(weights0, solver_factory):
+    """The BASELINE sine family (|w| ~ 1e5) that no fp32 pipeline can bring under 1e-5: the fp64
+    engine does, end to end, against the all-fp64 reference algebra."""
+    G, B = 40, 9
+    xp, yp, xb, yb = o.grid_problem(G)
+    Fm = np.stack([o.sine_source(xp, yp, seed=j) for j in range(B)], axis=1)
+    bcv = np.random.default_rng(0).uniform(-10, 10, B)
+    BC = np.tile(bcv[None], (xb.size, 1))
+    s = solver_factory(precision=torch.float64)
+    s.precompute(xp, yp, xb, yb)
+    u = s.solve(Fm, BC)[0]
+    U64, _ = o.solve_batch(o.precompute(xp, yp, xb, yb, weights0), Fm, BC)
+    worst = max(o.rel_l2(u[:, j].cpu().numpy(), U64[:, j]) for j in range(B))
+    print(f"\n[fp64 engine, rough sources] worst u rel-L2 vs reference algebra: {worst:.3e}")
+    assert worst < TOL_U
+    u1 = s.solve(Fm[:, 2], BC[:, 2])[0]
+    assert o.rel_l2(u1.cpu().numpy(), U64[:, [2]]) < TOL_U
