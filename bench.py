@@ -318,6 +318,8 @@ def run_ours(args):
         _lib.check(lib.fps_profile_enable(ctx, 1), "profile")
         _lib.check(lib.fps_profile_reset(ctx), "profile")
         ms_b = timed(lambda: solver.solve(Fm, bcv), 3)
+        u_cols = solver.u_pde_pred[:, :4].double().cpu().numpy()
+        f_cols, bc_cols = Fm[:, :4].double().cpu().numpy(), bcv[:4].double().cpu().numpy()
         pb = read_profile(solver)
         _lib.check(lib.fps_profile_enable(ctx, 0), "profile")
         batched = {"value": world * B / (ms_b * 1e-3), "unit": "solves/s", "ms_per_call": ms_b,
@@ -392,6 +394,16 @@ def run_ours(args):
                       f"sweeps, fp32, precompute+solve) took {dt:.1f} s on {threads} threads of {os.cpu_count()} cores",
             "forward_mode_port_points_per_s": 10000 / dt_fwd,
         }
+        if batched is not None:
+            # accuracy oracle of north_star: the reference's finite-difference solve (numeric_solver.py:39-160,
+            # restated exactly by a DST in oracle/fd_oracle.py) on the 512x512 grid of the batched config,
+            # metrics as analyze.py:107-119
+            from oracle import fd_oracle, fps_oracle
+
+            u_fd = fd_oracle.fd_solve_dst(512, f_cols, bc_cols)
+            out["cpu_baseline"]["accuracy_vs_fd_512x512"] = [
+                dict(fps_oracle.metrics(u_cols[:, j], u_fd[:, j]), rel_l2=fps_oracle.rel_l2(u_cols[:, j], u_fd[:, j]))
+                for j in range(u_cols.shape[1])]
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

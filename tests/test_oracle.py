@@ -84,3 +84,25 @@ def test_solve_batch_is_column_loop(weights0):
 def test_range_assert(weights0):
     with pytest.raises(AssertionError, match="x coordinates should be in"):
         o.precompute([0.5, 1.5], [0.5, 0.5], [0.0], [0.0], weights0)
+
+
+def test_fd_oracle_dst_equals_sparse_lu_restatement():
+    """numeric_solve restated with scipy.sparse (numeric_solver.py:104-151) vs the exact DST-I solve."""
+    from oracle import fd_oracle as fd
+
+    G = 20
+    xp, yp, _, _ = o.grid_problem(G)
+    f = o.sine_source(xp, yp, seed=4)
+    a = fd.fd_solve_sparse(G, f, -2.5)
+    b = fd.fd_solve_dst(G, f, -2.5)
+    assert o.rel_l2(a, b) < 1e-12
+    F = np.stack([f, 2 * f + 1], 1)
+    B = fd.fd_solve_dst(G, F, np.array([-2.5, 4.0]))
+    assert o.rel_l2(B[:, 0], a) < 1e-12 and B.shape == (G * G, 2)
+    # second-order convergence to the analytic solution of u_xx + u_yy = 50 sin(2 pi x) sin(3 pi y), u = 3 on the boundary
+    errs = []
+    for g in (16, 32):
+        x, y, _, _ = o.grid_problem(g)
+        exact = 3 - 50 / (13 * np.pi ** 2) * np.sin(2 * np.pi * x) * np.sin(3 * np.pi * y)
+        errs.append(o.rel_l2(fd.fd_solve_dst(g, 50 * np.sin(2 * np.pi * x) * np.sin(3 * np.pi * y), 3.0), exact))
+    assert 3.0 < errs[0] / errs[1] < 4.5
