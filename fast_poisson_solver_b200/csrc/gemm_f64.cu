@@ -270,10 +270,22 @@ int launch_atb_t(const fps_ctx* ctx, const TA* A, int64_t lda, int M, const TB* 
   const size_t tile_bytes = (size_t)GT * GT * sizeof(double);
   const int64_t max_ctas = (int64_t)(ctx->partial_bytes / tile_bytes);
   FPS_REQUIRE(ntiles <= max_ctas, "atb: %d tiles exceed the partial workspace", ntiles);
-  int64_t slices = ((int64_t)ctx->sm_count * 4 + ntiles - 1) / ntiles;
-  slices = std::min<int64_t>(slices, (n + 4 * GK - 1) / (4 * GK));
-  slices = std::min<int64_t>(slices, max_ctas / ntiles);
-  slices = std::max<int64_t>(slices, 1);
+  // Split the rows into `slices` so that tiles x slices fills whole waves of resident CTAs
+  // (66 Gram tiles x 9 slices on 148 SMs x 3 CTAs was 1.34 waves = 67 % wave efficiency).
+  static int occ = 0;
+  if (!occ) {
+    FPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, atb_f64_kernel<TA, TB>, GTHREADS, 0));
+    if (occ < 1) occ = 1;
+  }
+  const int64_t wave = (int64_t)ctx->sm_count * occ;
+  const int64_t smax = std::max<int64_t>(1, std::min<int64_t>({(int64_t)32, max_ctas / ntiles, (n + 4 * GK - 1) / (4 * GK)}));
+  int64_t slices = 1;
+  double best = 0.0;
+  for (int64_t sl = 1; sl <= smax; ++sl) {
+    const int64_t ctas = ntiles * sl;
+    const double eff = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
+    if (eff > best + 0.02) { best = eff; slices = sl; }
+  }
   const int64_t rps = ((n + slices - 1) / slices + GK - 1) / GK * GK;
   slices = (n + rps - 1) / rps;
   const int vecA = (lda % 4 == 0) && ((uintptr_t)A % 16 == 0);
@@ -332,71 +344,94 @@ int launch_colsum_d(const double* A, int64_t n, int64_t ld, double* s64, cudaStr
 // out(n x B) = A(n x FP) W(FP x B) + bias, fp64 accumulation.
 // Tile 64 rows x 64 columns, K steps of 32; A fragment loads want a row stride == 4 (mod 16).
 // ------------------------------------------------------------------------------------------------
-constexpr int NS_A = GK + 4;  // 36
+// Tile 128 rows x 128 columns, 8 warps (4 x 2, each 32 x 64), K steps of 16 with register prefetch of the
+// next A / W slabs; fragment loads want row strides == 4 (mod 16) doubles.
+constexpr int NT = 128, NK = 16, NS_A = NK + 4 /*20*/, NS_W = NT + 4 /*132*/, NTHREADS = 256;
 
 template <typename TA, typename TO>
-__global__ void __launch_bounds__(GTHREADS)
+__global__ void __launch_bounds__(NTHREADS)
 nn_f64_kernel(const TA* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
-              const double* __restrict__ bias, int B, TO* __restrict__ out, int64_t ldo) {
-  __shared__ __align__(16) double As[GT * NS_A];
-  __shared__ __align__(16) double Ws[GK * GS];
-  const int64_t r0 = (int64_t)blockIdx.x * GT;
-  const int c0 = blockIdx.y * GT;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+              const double* __restrict__ bias, int B, TO* __restrict__ out, int64_t ldo, int vecW) {
+  __shared__ __align__(16) double As[NT * NS_A];
+  __shared__ __align__(16) double Ws[NK * NS_W];
+  const int64_t r0 = (int64_t)blockIdx.y * NT;
+  const int c0 = blockIdx.x * NT;
+  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
   const int wi = warp / 2, wj = warp % 2;
   const int lr = lane / 4, lc = lane % 4;
-  double c[4][4][2];
+  double c[4][8][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    for (int j = 0; j < 8; ++j) c[i][j][0] = c[i][j][1] = 0.0;
 
-  for (int k0 = 0; k0 < FP; k0 += GK) {
-    __syncthreads();
-    // A tile: 64 rows x 32 k, 512 groups of 4, 4 per thread
+  // staging maps: A slab 128 rows x 16 k = 512 groups of 4 (2 per thread); W slab 16 k x 128 cols = 1024
+  // pairs (4 per thread)
+  TA ra[2][4];
+  double2 rw[4];
+  auto load_slab = [&](int k0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = q * GTHREADS + threadIdx.x;
-      const int r = idx / 8, kq = (idx % 8) * 4;
+    for (int q = 0; q < 2; ++q) {
+      const int idx = q * NTHREADS + t;
+      const int r = idx / 4, kq = (idx % 4) * 4;
       double o[4] = {0.0, 0.0, 0.0, 0.0};
       if (r0 + r < n) load4<TA>(A + (r0 + r) * ld + k0 + kq, 0, 4, true, o);
-      double2* d = reinterpret_cast<double2*>(As + r * NS_A + kq);
-      d[0] = make_double2(o[0], o[1]);
-      d[1] = make_double2(o[2], o[3]);
-    }
-    // W tile: 32 k x 64 columns of doubles, 2048 doubles, 16 per thread
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int idx = q * GTHREADS + threadIdx.x;
-      const int r = idx / GT, cc = idx % GT;
-      Ws[r * GS + cc] = (c0 + cc < B) ? W[(int64_t)(k0 + r) * ldw + c0 + cc] : 0.0;
+      for (int e = 0; e < 4; ++e) ra[q][e] = (TA)o[e];
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * NTHREADS + t;
+      const int r = idx / 64, cc = (idx % 64) * 2;
+      const double* p = W + (int64_t)(k0 + r) * ldw + c0 + cc;
+      if (vecW && c0 + cc + 1 < B) rw[q] = __ldg(reinterpret_cast<const double2*>(p));
+      else rw[q] = make_double2(c0 + cc < B ? __ldg(p) : 0.0, c0 + cc + 1 < B ? __ldg(p + 1) : 0.0);
+    }
+  };
+  load_slab(0);
+  for (int k0 = 0; k0 < FP; k0 += NK) {
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < GK / 4; ++kk) {
-      double a[4], b[4];
+    for (int q = 0; q < 2; ++q) {
+      const int idx = q * NTHREADS + t;
+      const int r = idx / 4, kq = (idx % 4) * 4;
+      double2* d = reinterpret_cast<double2*>(As + r * NS_A + kq);
+      d[0] = make_double2((double)ra[q][0], (double)ra[q][1]);
+      d[1] = make_double2((double)ra[q][2], (double)ra[q][3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * NTHREADS + t;
+      const int r = idx / 64, cc = (idx % 64) * 2;
+      *reinterpret_cast<double2*>(Ws + r * NS_W + cc) = rw[q];
+    }
+    __syncthreads();
+    if (k0 + NK < FP) load_slab(k0 + NK);
+#pragma unroll
+    for (int kk = 0; kk < NK / 4; ++kk) {
+      double a[4], b[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[(wi * 32 + i * 8 + lr) * NS_A + kk * 4 + lc];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Ws[(kk * 4 + lc) * GS + wj * 32 + j * 8 + lr];
+      for (int j = 0; j < 8; ++j) b[j] = Ws[(kk * 4 + lc) * NS_W + wj * 64 + j * 8 + lr];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma8x8x4(c[i][j][0], c[i][j][1], a[i], b[j]);
+        for (int j = 0; j < 8; ++j) dmma8x8x4(c[i][j][0], c[i][j][1], a[i], b[j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + wi * 32 + i * 8 + lr;
+    if (r >= n) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t r = r0 + wi * 32 + i * 8 + lr;
-      const int cc = c0 + wj * 32 + j * 8 + lc * 2;
-      if (r < n) {
+    for (int j = 0; j < 8; ++j) {
+      const int cc = c0 + wj * 64 + j * 8 + lc * 2;
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-          if (cc + e < B) out[r * ldo + cc + e] = (TO)(c[i][j][e] + (bias ? bias[cc + e] : 0.0));
-      }
+      for (int e = 0; e < 2; ++e)
+        if (cc + e < B) out[r * ldo + cc + e] = (TO)(c[i][j][e] + (bias ? bias[cc + e] : 0.0));
     }
+  }
 }
 
 // Few right-hand sides: one warp per row, W columns staged in shared memory; HBM-bound on A.
@@ -463,8 +498,10 @@ int launch_reconstruct_t(const fps_ctx* ctx, const TA* A, int64_t n, int64_t ld,
     else if (B == 2) nn_small_kernel<2, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
     else nn_small_kernel<4, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
   } else {
-    dim3 grid((unsigned)((n + GT - 1) / GT), (unsigned)((B + GT - 1) / GT));
-    nn_f64_kernel<TA, TO><<<grid, GTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
+    // column tiles fastest: the CTAs that share an A row block run together and hit it in L2
+    dim3 grid((unsigned)((B + NT - 1) / NT), (unsigned)((n + NT - 1) / NT));
+    const int vecW = (ldw % 2 == 0) && ((uintptr_t)W % 16 == 0);
+    nn_f64_kernel<TA, TO><<<grid, NTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo, vecW);
   }
   count_launch();
   FPS_CUDA(cudaGetLastError());
