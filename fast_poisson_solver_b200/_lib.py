@@ -57,6 +57,8 @@ SIGNATURES = {
     "fps_colsum_accum_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fps_project_rhs_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "fps_reconstruct_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "fps_sine_sources": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "fps_sine_sources_f64": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
     "fps_launch_count": (_i64, []),
     "fps_profile_enable": (_i32, [_vp, _i32]),
     "fps_profile_reset": (_i32, [_vp]),

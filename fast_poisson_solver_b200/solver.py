@@ -217,6 +217,7 @@ class Solver:
             self.precompute_file = os.path.join(self.precompute_path, name + ".pkl")
         with torch.cuda.device(self._dev_index):
             x64 = [_as_f64_column(v, self._tdev) for v in (x_pde, y_pde, x_bc, y_bc)]
+            self._xy64 = x64
             self.x_pde, self.y_pde, self.x_bc, self.y_bc = [t.to(self.precision).reshape(-1, 1) for t in x64]
             self.x_tot = torch.cat([self.x_pde, self.x_bc], dim=0)
             self.y_tot = torch.cat([self.y_pde, self.y_bc], dim=0)
@@ -403,6 +404,7 @@ class Solver:
             else:
                 self.lambda_pde = self.lambdas_pde[0]
 
+            self._W64, self._bias64 = W, bias
             self.w_out = W[:F].to(self.precision)
             self.bias = bias.to(self.precision).reshape(1, B)
             self.u_pred = U.to(self.precision)
@@ -414,6 +416,20 @@ class Solver:
         if self.verbose > 0:
             print("\nRun Successful:", t1 - t0, "seconds\n")
         return self.u_pred, self.u_pde_pred, self.u_bc_pred, self.f_pred, t1 - t0
+
+    def evaluate(self, x, y):
+        """Extension: the last solution u(x, y) = H(x, y) w + b at arbitrary points of [0,1]^2, (n, B)."""
+        if not hasattr(self, "_W64"):
+            raise RuntimeError("call solve() before evaluate()")
+        with torch.cuda.device(self._dev_index):
+            x64, y64 = _as_f64_column(x, self._tdev), _as_f64_column(y, self._tdev)
+            Hq, _ = self._features(x64, y64, False)
+            B = self._W64.shape[1]
+            out = torch.empty((x64.numel(), B), dtype=self._fdtype, device=self._tdev)
+            _lib.check(self._fn("fps_reconstruct")(self._ctx, Hq.data_ptr(), x64.numel(), FP, self._W64.data_ptr(), B,
+                                                   self._bias64.data_ptr(), B, out.data_ptr(), B, self._stream()),
+                       "fps_reconstruct(evaluate)")
+            return out.to(self.precision)
 
     def _reconstruct(self, W, bias, B, U, Fp, st):
         n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]

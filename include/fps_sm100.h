@@ -125,6 +125,15 @@ int fps_project_rhs_f64(fps_ctx* ctx, const double* DH, int64_t n, int64_t ld, c
 int fps_reconstruct_f64(fps_ctx* ctx, const double* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
                         const double* bias64, int B, double* out, int64_t ldo, void* stream);
 
+/* ---- on-device synthetic sources (data_utils/source_functions.py:24-73, the 'sin' family) ---------
+ * F[r, j] = sum_t s * sin(k1*pi*(x_r - o1)) * (use_cos ? cos : sin)(k2*pi*(y_r - o2)),  j < B, t < n_terms
+ * params: device (B, n_terms, 6) float64 = {k1, o1, k2, o2, s, use_cos}; terms with s == 0 are skipped.
+ * Writes the (n, B) right-hand-side block that fps_project_rhs consumes; x, y are device float64.   */
+int fps_sine_sources(fps_ctx* ctx, const double* x, const double* y, int64_t n, const double* params,
+                     int n_terms, int B, float* F, int64_t ldf, void* stream);
+int fps_sine_sources_f64(fps_ctx* ctx, const double* x, const double* y, int64_t n, const double* params,
+                         int n_terms, int B, double* F, int64_t ldf, void* stream);
+
 /* ---- instrumentation (bench.py / profiles) ----------------------------------------------------
  * fps_launch_count: number of kernels this library has launched in this process (all contexts).
  * fps_profile_enable(ctx, 1): bracket every kernel launch of ctx with CUDA events on its stream.

@@ -328,3 +328,22 @@ def test_f64_rough_sources_meet_1e5_end_to_end(weights0, solver_factory):
     assert worst < TOL_U
     u1 = s.solve(Fm[:, 2], BC[:, 2])[0]
     assert o.rel_l2(u1.cpu().numpy(), U64[:, [2]]) < TOL_U
+
+
+def test_device_sine_sources_and_evaluate(solver_factory):
+    from fast_poisson_solver_b200.sources import sine_params, sine_sources, sine_sources_numpy
+
+    xp, yp, xb, yb = o.grid_problem(36)
+    s = solver_factory()
+    s.precompute(xp, yp, xb, yb)
+    par = sine_params(37, seed=3)
+    Fd = sine_sources(s, par)
+    Fh = sine_sources_numpy(xp, yp, par)
+    assert Fd.shape == (xp.size, 37) and Fd.dtype == torch.float32
+    assert np.allclose(Fd.cpu().numpy(), Fh, rtol=1e-6, atol=1e-4)
+    u, u_pde, _, _, _ = s.solve(Fd[:, :3], np.array([1.0, -1.0, 0.5]))
+    # u(x, y) evaluated at the collocation points reproduces u_pde; elsewhere it is finite and smooth
+    again = s.evaluate(xp, yp)
+    assert o.rel_l2(again.cpu().numpy(), u_pde.cpu().numpy()) < 1e-6
+    mid = s.evaluate(np.array([0.5, 0.25]), np.array([0.5, 0.75]))
+    assert mid.shape == (2, 3) and torch.isfinite(mid).all()
