@@ -351,11 +351,11 @@ constexpr int NT = 128, NK = 16, NS_A = NK + 4 /*20*/, NS_W = NT + 4 /*132*/, NT
 template <typename TA, typename TO>
 __global__ void __launch_bounds__(NTHREADS)
 nn_f64_kernel(const TA* __restrict__ A, int64_t n, int64_t ld, const double* __restrict__ W, int64_t ldw,
-              const double* __restrict__ bias, int B, TO* __restrict__ out, int64_t ldo, int vecW) {
+              const double* __restrict__ bias, int B, TO* __restrict__ out, int64_t ldo, int vecW, int col_tiles) {
   __shared__ __align__(16) double As[NT * NS_A];
   __shared__ __align__(16) double Ws[NK * NS_W];
-  const int64_t r0 = (int64_t)blockIdx.y * NT;
-  const int c0 = blockIdx.x * NT;
+  const int64_t r0 = (int64_t)(blockIdx.x / col_tiles) * NT;  // 1-D grid: the row-tile count can exceed 65535
+  const int c0 = (int)(blockIdx.x % col_tiles) * NT;
   const int t = threadIdx.x, warp = t / 32, lane = t % 32;
   const int wi = warp / 2, wj = warp % 2;
   const int lr = lane / 4, lc = lane % 4;
@@ -499,9 +499,11 @@ int launch_reconstruct_t(const fps_ctx* ctx, const TA* A, int64_t n, int64_t ld,
     else nn_small_kernel<4, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);
   } else {
     // column tiles fastest: the CTAs that share an A row block run together and hit it in L2
-    dim3 grid((unsigned)((B + NT - 1) / NT), (unsigned)((n + NT - 1) / NT));
+    const int col_tiles = (B + NT - 1) / NT;
+    const int64_t ctas = (int64_t)col_tiles * ((n + NT - 1) / NT);
+    FPS_REQUIRE(ctas < ((int64_t)1 << 31), "reconstruct: too many tiles (%lld)", (long long)ctas);
     const int vecW = (ldw % 2 == 0) && ((uintptr_t)W % 16 == 0);
-    nn_f64_kernel<TA, TO><<<grid, NTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo, vecW);
+    nn_f64_kernel<TA, TO><<<(unsigned)ctas, NTHREADS, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo, vecW, col_tiles);
   }
   count_launch();
   FPS_CUDA(cudaGetLastError());

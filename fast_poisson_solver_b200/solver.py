@@ -227,6 +227,11 @@ class Solver:
                 assert torch.min(self.y_tot) >= 0 and torch.max(self.y_tot) <= 1, \
                     "y coordinates should be in [0, 1]. Please rescale."
 
+            # drop the previous domain's feature matrices first: at 16M points they are 47 GB each
+            for name in ("H", "DH", "Dht", "H_bc", "Ht_bc", "_Hp", "_DHp", "_Hbcp", "u_pred", "u_pde_pred", "u_bc_pred",
+                         "f_pred", "f", "bc"):
+                if hasattr(self, name):
+                    setattr(self, name, None)
             if load and os.path.isfile(self.precompute_file):
                 self._load_precomputed()
             else:
