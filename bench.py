@@ -364,7 +364,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "kernels_ms_per_step": kernels_ms,
-        "roofline": {"kernel": "layer_tc_kernel<4,false> (hidden 700x700 layer, 4 streams, 3xTF32 tcgen05)",
+        "roofline": {"kernel": "layer_tc_pair_kernel<4,false> (hidden 700x700 layer, 4 streams, 3xTF32 tcgen05 cta_group::2)",
                      "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf32_peak if achieved else None,
                      "issued_frac": 3 * achieved * (768 / 700) * (704 / 700) / tf32_peak if achieved else None,
@@ -373,7 +373,10 @@ def run_ours(args):
                                     "8192^3, allow_tf32): `peak` = sustained (back to back 1.5 s, the kernel is timed inside "
                                     "a long step), `peak_burst` = best of 10; MEASURED_PEAKS.json has no TF32 entry "
                                     "(bf16 there: %s burst / %s sustained)" % (peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained")),
-                     "launches": int(hid_n), "avg_launch_ms": hid_ms / hid_n if hid_n else None, "traffic": None},
+                     "launches": int(hid_n), "avg_launch_ms": hid_ms / hid_n if hid_n else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one 18 944-point launch, ncu --set full,
+                     # profiles/r01b_layer_tc_ncu_full_summary.csv (algorithmic: 427 MB in + 424 MB out + 4 MB weights)
+                     "traffic": 846.7e6, "traffic_unit": "bytes/launch (ncu)"},
         "other_rooflines": {
             "features_all_layers": {"achieved": n_pts * FLOP_PER_POINT_FEATURES / (feat_ms * 1e-3) / 1e12,
                                     "peak": tf32_peak, "unit": "TFLOP/s (algorithmic, 3 MMAs issued per product)"},
