@@ -15,7 +15,7 @@ constexpr int FOURIER_THREADS = 224;  // 200 frequency lanes + 8 pad lanes, roun
 template <int S>
 __global__ void __launch_bounds__(FOURIER_THREADS)
 fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
-               const double* __restrict__ ffm, float* __restrict__ hi, float* __restrict__ lo) {
+               const double* __restrict__ ffm, const ActPlanes P, const StreamScale sc) {
   const int j = threadIdx.x;
   double f0 = 0, f1 = 0, c = 0, beta = 0;
   if (j < NFREQ) {
@@ -33,25 +33,23 @@ fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64
       sincos(z, &sn, &cs);
       sn *= c;
       cs *= c;
-      split_store(hi + row + j, lo + row + j, (float)sn);
-      split_store(hi + row + NFREQ + j, lo + row + NFREQ + j, (float)cs);
+      store_planes(P, row + j, (float)sn, sc.s[0]);
+      store_planes(P, row + NFREQ + j, (float)cs, sc.s[0]);
       if (S == 4) {
-        split_store(hi + row + K0P + j, lo + row + K0P + j, (float)(cs * f0));
-        split_store(hi + row + K0P + NFREQ + j, lo + row + K0P + NFREQ + j, (float)(-sn * f0));
-        split_store(hi + row + 2 * K0P + j, lo + row + 2 * K0P + j, (float)(cs * f1));
-        split_store(hi + row + 2 * K0P + NFREQ + j, lo + row + 2 * K0P + NFREQ + j, (float)(-sn * f1));
-        split_store(hi + row + 3 * K0P + j, lo + row + 3 * K0P + j, (float)(-k2 * sn));
-        split_store(hi + row + 3 * K0P + NFREQ + j, lo + row + 3 * K0P + NFREQ + j, (float)(-k2 * cs));
+        store_planes(P, row + K0P + j, (float)(cs * f0), sc.s[1]);
+        store_planes(P, row + K0P + NFREQ + j, (float)(-sn * f0), sc.s[1]);
+        store_planes(P, row + 2 * K0P + j, (float)(cs * f1), sc.s[2]);
+        store_planes(P, row + 2 * K0P + NFREQ + j, (float)(-sn * f1), sc.s[2]);
+        store_planes(P, row + 3 * K0P + j, (float)(-k2 * sn), sc.s[3]);
+        store_planes(P, row + 3 * K0P + NFREQ + j, (float)(-k2 * cs), sc.s[3]);
       }
     } else if (j < NFREQ + 8) {
       // zero the K padding (columns 400..415) of every stream row
       const int c0 = K0 + 2 * (j - NFREQ);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        hi[row + s * K0P + c0] = 0.f;
-        hi[row + s * K0P + c0 + 1] = 0.f;
-        lo[row + s * K0P + c0] = 0.f;
-        lo[row + s * K0P + c0 + 1] = 0.f;
+        store_planes(P, row + s * K0P + c0, 0.f, 1.f);
+        store_planes(P, row + s * K0P + c0 + 1, 0.f, 1.f);
       }
     }
   }
@@ -62,9 +60,9 @@ int launch_fourier(const fps_ctx* ctx, const double* x, const double* y, int64_t
   if (n <= 0) return 0;
   int64_t blocks = n < (int64_t)ctx->sm_count * 8 ? n : (int64_t)ctx->sm_count * 8;
   if (streams == 4)
-    fourier_kernel<4><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out.hi, out.lo);
+    fourier_kernel<4><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0]);
   else
-    fourier_kernel<1><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out.hi, out.lo);
+    fourier_kernel<1><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0]);
   count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;

@@ -1,5 +1,6 @@
 // Shared declarations for libfps_sm100.so (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -25,16 +26,35 @@ constexpr int NSTREAM = 4;        // value, d/dx, d/dy, laplacian
 //   hi = value with the low 13 mantissa bits cleared (exactly a TF32 number)
 //   lo = value - hi (exact in fp32; its top 11 bits are what the tensor core consumes)
 // so that hi + lo reproduces the fp32 activation exactly and A*B ~ Ahi*Bhi + Ahi*Blo + Alo*Bhi.
+//
+// f16 = 1 ("FP16x2 split", the production format): the same value is stored as two fp16 planes of a
+// power-of-two scaled copy t = v * S (S per layer input and stream, chosen so that typical |t| ~ 1):
+//   hi16 = fp16(t),  lo16 = fp16(t - hi16)            (22+ significant bits, 4 bytes per element)
+// and the contraction runs as three kind::f16 MMAs  Whi*Ahi + Whi*Alo + Wlo*Ahi  with the weights split the
+// same way at scale W16_SCALE; the epilogue multiplies by 1 / (W16_SCALE * S).  Half the operand bytes of
+// the TF32 format and half the tensor-core cycles, at the same ~2^-22 product accuracy (fp16 and tf32 both
+// carry 11 significand bits); values far below the scale fall into fp16 subnormals, whose 6e-8 absolute
+// spacing relative to |t| ~ 1 is still fp32 grade for the dot product.
 struct ActPlanes {
   float* hi;
   float* lo;
+  __half* hi16;
+  __half* lo16;
+  int f16;
 };
+constexpr float W16_SCALE = 16.0f;   // |w| <= 1/sqrt(400) = 0.05 -> |w * 16| < 1
 
 struct Layer {
   float* w_hi;   // (FPW, Kp) row-major, K-major == torch weight[out][in], zero padded
   float* w_lo;
   float* bias;   // (FPW) zero padded
+  __half* w_hi16;  // (FPW, Kp) fp16(w * W16_SCALE)
+  __half* w_lo16;  // (FPW, Kp) fp16(w * W16_SCALE - w_hi16)
   int Kp;        // padded K (K0P for layer 0, FP otherwise)
+};
+
+struct StreamScale {  // per-stream power-of-two scales of one layer's input planes (f16 format)
+  float s[4];
 };
 
 }  // namespace fps
@@ -49,6 +69,8 @@ struct fps_ctx {
   int device;
   int engine;
   int chunk;              // points per wave
+  int f16;                // 1: FP16x2-split operand planes (production), 0: 3xTF32 planes
+  fps::StreamScale act_scale[fps::NLAYER];  // input scales per layer (f16 format)
   int sm_count;
   fps::Layer layer[fps::NLAYER];
   double* ffm;            // 4*NFREQ doubles: F0 | F1 | coefficients | biases
@@ -126,6 +148,25 @@ __device__ __forceinline__ void tanh_streams(float a, float ax, float ay, float 
   hx = d1 * ax;
   hy = d1 * ay;
   hl = fmaf(d2, fmaf(ax, ax, ay * ay), d1 * al);
+}
+
+// store one activation value into the operand planes of the next layer (see ActPlanes)
+__device__ __forceinline__ void store_planes(const ActPlanes& P, size_t idx, float v, float scale) {
+  if (P.f16) {
+    const float t = v * scale;
+    const __half h = __float2half_rn(t);
+    P.hi16[idx] = h;
+    P.lo16[idx] = __float2half_rn(t - __half2float(h));
+  } else {
+    const float h = tf32_hi(v);
+    P.hi[idx] = h;
+    P.lo[idx] = v - h;
+  }
+}
+// read it back (SIMT cross-check engine)
+__device__ __forceinline__ float load_planes(const ActPlanes& P, size_t idx, float inv_scale) {
+  if (P.f16) return (__half2float(P.hi16[idx]) + __half2float(P.lo16[idx])) * inv_scale;
+  return P.hi[idx] + P.lo[idx];
 }
 
 __device__ __forceinline__ void split_store(float* hi, float* lo, float v) {

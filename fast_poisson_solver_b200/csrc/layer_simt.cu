@@ -16,10 +16,12 @@ constexpr int SBM = 128, SBN = 64, SBK = 16, STHREADS = 256;
 
 template <int S, bool LAST>
 __global__ void __launch_bounds__(STHREADS)
-layer_simt_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_lo, int Kp,
+layer_simt_kernel(const ActPlanes in, const StreamScale in_sc, int Kp,
                   const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
-                  float* __restrict__ out_hi, float* __restrict__ out_lo, float* __restrict__ H,
+                  const ActPlanes outp, const StreamScale out_sc, float* __restrict__ H,
                   float* __restrict__ DH, int64_t ld, int64_t rows) {
+  const float* __restrict__ in_hi = in.hi;
+  const float* __restrict__ in_lo = in.lo;
   __shared__ __align__(16) float As[SBK][SBM + 4];
   __shared__ __align__(16) float Bs[SBK][SBN + 4];
   const int t = threadIdx.x;
@@ -43,7 +45,24 @@ layer_simt_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_
 
   for (int k0 = 0; k0 < Kp; k0 += SBK) {
     float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
-    if (a_ok) {
+    if (a_ok && in.f16) {
+      // FP16x2-split planes: value = (hi16 + lo16) / scale[stream of this row]
+      const size_t base = (size_t)(row0 + a_row) * Kp + a_k + k0;
+      const float inv = 1.0f / in_sc.s[S == 4 ? (int)((row0 + a_row) & 3) : 0];
+      const uint4 qh = *reinterpret_cast<const uint4*>(in.hi16 + base);
+      const uint4 ql = *reinterpret_cast<const uint4*>(in.lo16 + base);
+      const __half2* hh = reinterpret_cast<const __half2*>(&qh);
+      const __half2* hl = reinterpret_cast<const __half2*>(&ql);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fh = __half22float2(hh[e]), fl = __half22float2(hl[e]);
+        v[2 * e] = (fh.x + fl.x) * inv;
+        v[2 * e + 1] = (fh.y + fl.y) * inv;
+      }
+      a0 = make_float4(v[0], v[1], v[2], v[3]);
+      a1 = make_float4(v[4], v[5], v[6], v[7]);
+    } else if (a_ok) {
       const float4 h0 = *reinterpret_cast<const float4*>(a_hi + k0);
       const float4 h1 = *reinterpret_cast<const float4*>(a_hi + k0 + 4);
       const float4 l0 = *reinterpret_cast<const float4*>(a_lo + k0);
@@ -93,15 +112,9 @@ layer_simt_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_
         *reinterpret_cast<float4*>(DH + p * ld + col) = make_float4(o[3][0], o[3][1], o[3][2], o[3][3]);
       } else {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          float4 hi4, lo4;
-          hi4.x = tf32_hi(o[s][0]); lo4.x = o[s][0] - hi4.x;
-          hi4.y = tf32_hi(o[s][1]); lo4.y = o[s][1] - hi4.y;
-          hi4.z = tf32_hi(o[s][2]); lo4.z = o[s][2] - hi4.z;
-          hi4.w = tf32_hi(o[s][3]); lo4.w = o[s][3] - hi4.w;
-          *reinterpret_cast<float4*>(out_hi + (r + s) * FP + col) = hi4;
-          *reinterpret_cast<float4*>(out_lo + (r + s) * FP + col) = lo4;
-        }
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) store_planes(outp, (size_t)(r + s) * FP + col + j, o[s][j], out_sc.s[s]);
       }
     }
   } else {
@@ -115,13 +128,8 @@ layer_simt_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_
       if (LAST) {
         *reinterpret_cast<float4*>(H + r * ld + col) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
-        float4 hi4, lo4;
-        hi4.x = tf32_hi(o[0]); lo4.x = o[0] - hi4.x;
-        hi4.y = tf32_hi(o[1]); lo4.y = o[1] - hi4.y;
-        hi4.z = tf32_hi(o[2]); lo4.z = o[2] - hi4.z;
-        hi4.w = tf32_hi(o[3]); lo4.w = o[3] - hi4.w;
-        *reinterpret_cast<float4*>(out_hi + r * FP + col) = hi4;
-        *reinterpret_cast<float4*>(out_lo + r * FP + col) = lo4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) store_planes(outp, (size_t)r * FP + col + j, o[j], out_sc.s[0]);
       }
     }
   }
@@ -134,8 +142,8 @@ int launch_layer_simt(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, in
   const int64_t rows = points * streams;
   dim3 grid((unsigned)((rows + SBM - 1) / SBM), FP / SBN);
 #define FPS_SIMT_LAUNCH(S_, LAST_)                                                                           \
-  layer_simt_kernel<S_, LAST_><<<grid, STHREADS, 0, st>>>(in.hi, in.lo, L.Kp, L.w_hi, L.w_lo, L.bias, out.hi, \
-                                                           out.lo, H, DH, ld, rows)
+  layer_simt_kernel<S_, LAST_><<<grid, STHREADS, 0, st>>>(in, ctx->act_scale[l], L.Kp, L.w_hi, L.w_lo, L.bias, out, \
+                                                           ctx->act_scale[l + 1 < NLAYER ? l + 1 : l], H, DH, ld, rows)
   if (streams == 4) {
     if (last) FPS_SIMT_LAUNCH(4, true); else FPS_SIMT_LAUNCH(4, false);
   } else {

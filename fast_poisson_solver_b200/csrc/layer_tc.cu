@@ -47,11 +47,9 @@ namespace fps {
 constexpr int TM = 128;                 // features per CTA tile (UMMA M per CTA)
 constexpr int TN = 256;                 // activation rows per tile (UMMA N)
 constexpr int TK = 16;                  // fp32 per K slab: 64-byte swizzled rows
-constexpr int UK = 8;                   // K per tcgen05.mma.kind::tf32
 constexpr int ROW_BYTES = TK * 4;       // shared-memory row = swizzle span (SWIZZLE_64B)
 constexpr int BOX_ROWS = 128;           // every TMA box is 128 rows x TK
 constexpr int BOX_BYTES = BOX_ROWS * ROW_BYTES;  // 8 KiB
-constexpr int SEG_SLABS = 128 / TK;     // K slabs accumulated inside the tensor core before promotion (K = 128)
 constexpr int TC_THREADS = 320;         // TMA warp, MMA warp, 8 accumulate/epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int N_FEAT_TILES = FPW / TM;  // 6
@@ -69,12 +67,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The TMEM-drained arrives are RELAXED on purpose: the default .release makes ptxas emit MEMBAR.ALL.GPU,
+// which waits for every outstanding global store of the epilogue (ncu: 19 % of all stall samples sat on
+// that fence).  Ordering of the TMEM reads is provided by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // arrive on the barrier at the same offset in the pair leader's shared memory (works from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -118,14 +119,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B, 8-row groups 512 B apart.
+// K-major swizzled shared-memory matrix descriptor: rows of RB bytes (= swizzle span), 8-row groups 8*RB
+// apart.  Swizzle mode field: 2 = 128B, 4 = 64B, 6 = 32B.
+template <int RB>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3ffff) >> 4);         // start address, 16-byte units
   d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;     // stride byte offset between 8-row groups
+  d |= (uint64_t)((8 * RB) >> 4) << 32;            // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
-  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61; // swizzle mode: 2 = 128B, 4 = 64B
+  d |= (uint64_t)(RB == 128 ? 2 : (RB == 64 ? 4 : 6)) << 61;
   return d;
 }
 
@@ -146,6 +149,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// kind::f16 (fp16 x fp16 -> fp32 accumulate), K = 16 per instruction: the two small cross terms
+template <int NCTA>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((TM * NCTA) >> 4) << 24);
+  if (NCTA == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
   }
@@ -178,6 +201,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_b16(uint32_t addr, __half v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__half_as_ushort(v)) : "memory");
+}
+// shared -> global bulk async copy of one contiguous row segment (bytes % 16 == 0, both 16-byte aligned)
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -187,10 +224,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
+// FPS_TC_DEBUG=9: cycle accounting of CTA 0 (developer instrumentation, read with fps_debug_tc_stats)
+__device__ unsigned long long g_tc_stats[8];
+#define TC_STAT_ADD(i, v) do { if (P.debug == 9 && blockIdx.x == 0) atomicAdd(&g_tc_stats[i], (unsigned long long)(v)); } while (0)
+
 struct TcParams {
   const float* bias;
-  float* out_hi;
-  float* out_lo;
+  ActPlanes out;
   float* H;
   float* DH;
   int64_t ld;
@@ -199,15 +239,22 @@ struct TcParams {
   int row_tiles;  // ceil(rows / 256)
   int debug;      // FPS_TC_DEBUG experiments (0 = production)
   int seg;        // K slabs per tensor-core accumulation segment
+  float in_inv[4]; // per stream: 1 / (W16_SCALE * input scale) (FP16x2 format), else 1
+  float out_sc[4]; // per stream: scale of the next layer's input planes
   float gain;      // 1 + kappa(K_seg): first-order compensation of the accumulator truncation bias
   float gain_tail; // same for the shorter last segment of a tile
 };
 
-template <int S, bool LAST, int NCTA>
+// F16 = false: 3xTF32, planes hi32 / lo32, K slab = 16 floats.  F16 = true: FP16x2 split, planes hi16 / lo16,
+// K slab = 32 halves.  Either way a slab row is 64 bytes (SWIZZLE_64B), a box is 128 rows = 8 KiB, one MMA
+// covers 32 bytes of K, and the stage is {Ahi, Alo, Bhi.., Blo..}; only the tensor maps' element type, the
+// MMA kind and the K extent per slab differ.
+template <int S, bool LAST, int NCTA, bool F16>
 __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo,
                                               const CUtensorMap& tmAhi, const CUtensorMap& tmAlo, const TcParams& P) {
   constexpr int B_BOXES = TN / BOX_ROWS / NCTA;                   // activation boxes this CTA loads per plane
   constexpr int STAGE_BYTES = 2 * BOX_BYTES + 2 * B_BOXES * BOX_BYTES;  // {Ahi, Alo, Bhi.., Blo..}
+  constexpr int TKE = F16 ? 2 * TK : TK;                          // K elements per slab
   constexpr int STAGES = RING_BYTES / STAGE_BYTES;                // 4 (single CTA) or 6 (pair)
   static_assert(STAGES <= MAX_STAGES, "ring too deep for the barrier block");
 
@@ -269,12 +316,12 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
           if (rank == 0) mbar_expect_tx(full, STAGE_BYTES * NCTA);
-          tma_load_2d<NCTA>(sa, &tmWhi, full, kc * TK, ft * TM);
-          tma_load_2d<NCTA>(sa + BOX_BYTES, &tmWlo, full, kc * TK, ft * TM);
+          tma_load_2d<NCTA>(sa, &tmWhi, full, kc * TKE, ft * TM);
+          tma_load_2d<NCTA>(sa + BOX_BYTES, &tmWlo, full, kc * TKE, ft * TM);
 #pragma unroll
           for (int b = 0; b < B_BOXES; ++b) {
-            tma_load_2d<NCTA>(sa + (2 + b) * BOX_BYTES, &tmAhi, full, kc * TK, brow + b * BOX_ROWS);
-            tma_load_2d<NCTA>(sa + (2 + B_BOXES + b) * BOX_BYTES, &tmAlo, full, kc * TK, brow + b * BOX_ROWS);
+            tma_load_2d<NCTA>(sa + (2 + b) * BOX_BYTES, &tmAhi, full, kc * TKE, brow + b * BOX_ROWS);
+            tma_load_2d<NCTA>(sa + (2 + B_BOXES + b) * BOX_BYTES, &tmAlo, full, kc * TKE, brow + b * BOX_ROWS);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -284,27 +331,37 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
     // ================= MMA issuer (pair leader only) =================
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
+      const long long t_loop = clock64();
       for (int t = group; t < total_tiles; t += ngroups) {
+        TC_STAT_ADD(6, 1);
         for (int kc0 = 0; kc0 < P.nk; kc0 += P.seg) {
           const int kc1 = (kc0 + P.seg < P.nk) ? kc0 + P.seg : P.nk;
+          const long long t_a = clock64();
           mbar_wait(bar_tempty + 8 * abuf, aphase ^ 1);  // accumulate warps have drained this buffer
+          TC_STAT_ADD(1, clock64() - t_a);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + abuf * TN;
           for (int kc = kc0; kc < kc1; ++kc) {
+            const long long t_b = clock64();
             mbar_wait(bar_full + 8 * stage, phase);
+            TC_STAT_ADD(0, clock64() - t_b);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + BOX_BYTES);
-            const uint64_t b_hi = umma_desc(sa + 2 * BOX_BYTES), b_lo = umma_desc(sa + (2 + B_BOXES) * BOX_BYTES);
+            const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), a_lo = umma_desc<ROW_BYTES>(sa + BOX_BYTES);
+            const uint64_t b_hi = umma_desc<ROW_BYTES>(sa + 2 * BOX_BYTES),
+                           b_lo = umma_desc<ROW_BYTES>(sa + (2 + B_BOXES) * BOX_BYTES);
 #pragma unroll
-            for (int j = 0; j < TK / UK; ++j) {
-              const uint64_t adv = (uint64_t)((j * UK * 4) >> 4);  // +32 bytes per k step inside the swizzle row
-              if (P.debug != 1) {
-                umma_tf32<NCTA>(d_tmem, a_lo + adv, b_hi + adv, (kc > kc0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < ROW_BYTES / 32; ++j) {
+              const uint64_t adv = (uint64_t)((j * 32) >> 4);  // +32 bytes of K per MMA inside the swizzle row
+              const uint32_t first = (kc > kc0 || j > 0) ? 1u : 0u;
+              if (F16) {
+                umma_f16<NCTA>(d_tmem, a_lo + adv, b_hi + adv, first);
+                umma_f16<NCTA>(d_tmem, a_hi + adv, b_lo + adv, 1u);
+                umma_f16<NCTA>(d_tmem, a_hi + adv, b_hi + adv, 1u);
+              } else {
+                umma_tf32<NCTA>(d_tmem, a_lo + adv, b_hi + adv, first);
                 umma_tf32<NCTA>(d_tmem, a_hi + adv, b_lo + adv, 1u);
                 umma_tf32<NCTA>(d_tmem, a_hi + adv, b_hi + adv, 1u);
-              } else {
-                umma_tf32<NCTA>(d_tmem, a_hi + adv, b_hi + adv, (kc > kc0 || j > 0) ? 1u : 0u);
               }
             }
             umma_commit<NCTA>(bar_empty + 8 * stage);  // smem slot is free once these MMAs retire
@@ -314,6 +371,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           if (++abuf == 2) { abuf = 0; aphase ^= 1; }
         }
       }
+      TC_STAT_ADD(2, clock64() - t_loop);
     }
   } else {
     // ================= accumulate + epilogue (warps 2..9) =================
@@ -323,13 +381,16 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
     for (int t = group; t < total_tiles; t += ngroups) {
       const int ft = (t % FT_GROUPS) * NCTA + rank, rt = t / FT_GROUPS;
       const int f = ft * TM + quad * 32 + lane;  // this thread's output feature
-      const bool f_ok = f < FP;                  // features 704..767 are tile padding
+
       const float bias = P.bias[f];
       float acc[TN / 2];
 #pragma unroll
       for (int i = 0; i < TN / 2; ++i) acc[i] = 0.f;
       for (int kc0 = 0; kc0 < P.nk; kc0 += P.seg) {
+        const long long t_c = clock64();
         mbar_wait(bar_tfull + 8 * abuf, aphase);
+        const long long t_d = clock64();
+        if (warp == 2 && lane == 0) TC_STAT_ADD(3, t_d - t_c);
         tc_fence_after();
         const uint32_t taddr = tmem_base + abuf * TN + half * (TN / 2) + ((uint32_t)(quad * 32) << 16);
         const float g = (kc0 + P.seg <= P.nk) ? P.gain : P.gain_tail;
@@ -347,15 +408,21 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           if (NCTA == 1) mbar_arrive(bar_tempty + 8 * abuf); else mbar_arrive_leader(bar_tempty + 8 * abuf);
         }
         if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+        if (warp == 2 && lane == 0) TC_STAT_ADD(4, clock64() - t_d);
       }
+      const long long t_e = clock64();
+      // ---- epilogue: tanh recurrences, split into the next layer's operand planes, 128-byte coalesced stores
+      // (a shared-memory staged variant with cp.async.bulk stores was measured SLOWER: 29.5 vs 25.1 ms)
       const int64_t r0 = (int64_t)rt * TN + half * (TN / 2);
+      const bool f_ok = f < FP;  // features 704..767 are tile padding
       if (S == 4) {
 #pragma unroll
         for (int q = 0; q < TN / 8; ++q) {
           const int64_t r = r0 + q * 4;
           float h, hx, hy, hl;
-          tanh_streams(acc[4 * q] + bias, acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3], h, hx, hy, hl);
-          if (f_ok && r < P.rows) {
+          tanh_streams(fmaf(acc[4 * q], P.in_inv[0], bias), acc[4 * q + 1] * P.in_inv[1], acc[4 * q + 2] * P.in_inv[2],
+                       acc[4 * q + 3] * P.in_inv[3], h, hx, hy, hl);
+          if (f_ok && r < P.rows && !(P.debug == 4 && h != 123.456f)) {
             if (LAST) {
               const int64_t p = r >> 2;
               P.H[p * P.ld + f] = h;
@@ -363,11 +430,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
             } else {
               const float o[4] = {h, hx, hy, hl};
 #pragma unroll
-              for (int s = 0; s < 4; ++s) {
-                const float hi = tf32_hi(o[s]);
-                P.out_hi[(r + s) * FP + f] = hi;
-                P.out_lo[(r + s) * FP + f] = o[s] - hi;
-              }
+              for (int s = 0; s < 4; ++s) store_planes(P.out, (size_t)(r + s) * FP + f, o[s], P.out_sc[s]);
             }
           }
         }
@@ -375,18 +438,14 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
 #pragma unroll
         for (int q = 0; q < TN / 2; ++q) {
           const int64_t r = r0 + q;
-          const float h = tanhf(acc[q] + bias);
+          const float h = tanhf(fmaf(acc[q], P.in_inv[0], bias));
           if (f_ok && r < P.rows) {
-            if (LAST) {
-              P.H[r * P.ld + f] = h;
-            } else {
-              const float hi = tf32_hi(h);
-              P.out_hi[r * FP + f] = hi;
-              P.out_lo[r * FP + f] = h - hi;
-            }
+            if (LAST) P.H[r * P.ld + f] = h;
+            else store_planes(P.out, (size_t)r * FP + f, h, P.out_sc[0]);
           }
         }
       }
+      if (warp == 2 && lane == 0) TC_STAT_ADD(5, clock64() - t_e);
     }
   }
 
@@ -402,20 +461,20 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
   }
 }
 
-template <int S, bool LAST>
+template <int S, bool LAST, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                 const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                 const TcParams P) {
-  layer_tc_body<S, LAST, 1>(tmWhi, tmWlo, tmAhi, tmAlo, P);
+  layer_tc_body<S, LAST, 1, F16>(tmWhi, tmWlo, tmAhi, tmAlo, P);
 }
 
-template <int S, bool LAST>
+template <int S, bool LAST, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 layer_tc_pair_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                      const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                      const TcParams P) {
-  layer_tc_body<S, LAST, 2>(tmWhi, tmWlo, tmAhi, tmAlo, P);
+  layer_tc_body<S, LAST, 2, F16>(tmWhi, tmWlo, tmAhi, tmAlo, P);
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------------------
@@ -424,23 +483,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct TcState {
-  CUtensorMap w_hi[NLAYER], w_lo[NLAYER];
-  CUtensorMap act_hi[2][2], act_lo[2][2];  // [buffer][0: K = K0P, 1: K = FP]
+  CUtensorMap w_hi[NLAYER], w_lo[NLAYER], w_hi16[NLAYER], w_lo16[NLAYER];
+  CUtensorMap act_hi[2][2], act_lo[2][2], act_hi16[2][2], act_lo16[2][2];  // [buffer][0: K = K0P, 1: K = FP]
   int pair;
 };
 
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64_t K, uint64_t rows) {
+// 2-D K-major map: dims {K, rows}, box {64 bytes of K, 128 rows}, SWIZZLE_64B (16 floats or 32 halves per row)
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, bool half) {
+  const uint64_t esz = half ? 2 : 4;
   cuuint64_t dims[2] = {K, rows};
-  cuuint64_t strides[1] = {K * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)BOX_ROWS};
+  cuuint64_t strides[1] = {K * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)BOX_ROWS};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for K=%llu rows=%llu", (int)r, (unsigned long long)K,
-              (unsigned long long)rows);
+    set_error("cuTensorMapEncodeTiled failed (%d) for K=%llu rows=%llu half=%d", (int)r, (unsigned long long)K,
+              (unsigned long long)rows, (int)half);
     return 1;
   }
   return 0;
@@ -450,6 +511,14 @@ template <typename Kern>
 static int set_smem(Kern k) {
   FPS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   return 0;
+}
+
+template <bool F16>
+static int set_smem_all() {
+  return set_smem(layer_tc_kernel<4, false, F16>) || set_smem(layer_tc_kernel<4, true, F16>) ||
+         set_smem(layer_tc_kernel<1, false, F16>) || set_smem(layer_tc_kernel<1, true, F16>) ||
+         set_smem(layer_tc_pair_kernel<4, false, F16>) || set_smem(layer_tc_pair_kernel<4, true, F16>) ||
+         set_smem(layer_tc_pair_kernel<1, false, F16>) || set_smem(layer_tc_pair_kernel<1, true, F16>);
 }
 
 int tc_init(fps_ctx* ctx) {
@@ -463,29 +532,41 @@ int tc_init(fps_ctx* ctx) {
   s->pair = getenv("FPS_TC_PAIR") ? atoi(getenv("FPS_TC_PAIR")) : 1;
   for (int l = 0; l < NLAYER; ++l) {
     const Layer& L = ctx->layer[l];
-    if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, FPW)) return 1;
-    if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, FPW)) return 1;
+    if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, FPW, false)) return 1;
+    if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, FPW, false)) return 1;
+    if (make_map(enc, &s->w_hi16[l], L.w_hi16, L.Kp, FPW, true)) return 1;
+    if (make_map(enc, &s->w_lo16[l], L.w_lo16, L.Kp, FPW, true)) return 1;
   }
   const uint64_t cap_rows = (uint64_t)ctx->chunk * NSTREAM;
   for (int b = 0; b < 2; ++b) {
-    // a plane holds cap_rows x FP floats; viewed with K = K0P it has room for more rows, but the same
+    // a plane holds cap_rows x FP elements; viewed with K = K0P it has room for more rows, but the same
     // row capacity is all a wave ever uses
-    if (make_map(enc, &s->act_hi[b][0], ctx->act[b].hi, K0P, cap_rows)) return 1;
-    if (make_map(enc, &s->act_lo[b][0], ctx->act[b].lo, K0P, cap_rows)) return 1;
-    if (make_map(enc, &s->act_hi[b][1], ctx->act[b].hi, FP, cap_rows)) return 1;
-    if (make_map(enc, &s->act_lo[b][1], ctx->act[b].lo, FP, cap_rows)) return 1;
+    const uint64_t Ks[2] = {(uint64_t)K0P, (uint64_t)FP};
+    for (int kv = 0; kv < 2; ++kv) {
+      if (make_map(enc, &s->act_hi[b][kv], ctx->act[b].hi, Ks[kv], cap_rows, false)) return 1;
+      if (make_map(enc, &s->act_lo[b][kv], ctx->act[b].lo, Ks[kv], cap_rows, false)) return 1;
+      if (make_map(enc, &s->act_hi16[b][kv], ctx->act[b].hi16, Ks[kv], cap_rows, true)) return 1;
+      if (make_map(enc, &s->act_lo16[b][kv], ctx->act[b].lo16, Ks[kv], cap_rows, true)) return 1;
+    }
   }
-  if (set_smem(layer_tc_kernel<4, false>) || set_smem(layer_tc_kernel<4, true>) ||
-      set_smem(layer_tc_kernel<1, false>) || set_smem(layer_tc_kernel<1, true>) ||
-      set_smem(layer_tc_pair_kernel<4, false>) || set_smem(layer_tc_pair_kernel<4, true>) ||
-      set_smem(layer_tc_pair_kernel<1, false>) || set_smem(layer_tc_pair_kernel<1, true>))
-    return 1;
+  if (set_smem_all<false>() || set_smem_all<true>()) return 1;
   return 0;
 }
 
 void tc_destroy(fps_ctx* ctx) {
   delete static_cast<TcState*>(ctx->tc_state);
   ctx->tc_state = nullptr;
+}
+
+// Truncation-bias compensation (see header): the tensor core rounds the fp32 accumulator toward zero after
+// every MMA, which shrinks a segment sum by kappa on average.  Measured on B200 against the fp64 oracle
+// (tools/calibrate_kappa.py) for the 3xTF32 scheme (3 MMAs per 8-wide k step): 4.2 ulp at K=32, 6 ulp at
+// K=64, 9 ulp at K=128, i.e. kappa(K) = 4.2 * 2^-23 * (K/32)^0.55.  The TF32 + 2xFP16 scheme issues 2 MMAs
+// per 8 k, so the same law is evaluated at 2/3 of the MMA count.  FPS_TC_KAPPA overrides (calibration).
+static float kappa_of(int kseg, bool f16) {
+  // 3xTF32: 4.2 ulp at K = 32 (48 MMAs per K = 128); FP16x2 split: 3.0e-7 at K = 128 (24 MMAs, calibrated)
+  if (f16) return 3.0e-7f * powf((float)kseg / 128.f, 0.55f);
+  return 4.2f * 1.1920929e-7f * powf((float)kseg / 32.f, 0.55f);
 }
 
 int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int64_t points, int streams, bool last,
@@ -497,48 +578,53 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   const int b = (in.hi == ctx->act[0].hi) ? 0 : 1;
   FPS_REQUIRE(in.hi == ctx->act[b].hi, "layer_tc: input planes must be the context's workspace");
   const int kv = (L.Kp == K0P) ? 0 : 1;
+  const bool f16 = ctx->f16 != 0;
   TcParams P;
   P.bias = L.bias;
-  P.out_hi = out.hi;
-  P.out_lo = out.lo;
+  P.out = out;
   P.H = H;
   P.DH = DH;
   P.ld = ld;
   P.rows = points * streams;
-  P.nk = L.Kp / TK;
+  P.nk = L.Kp / (f16 ? 2 * TK : TK);
+  for (int i = 0; i < 4; ++i) {
+    P.in_inv[i] = f16 ? 1.0f / (W16_SCALE * ctx->act_scale[l].s[i]) : 1.0f;
+    P.out_sc[i] = ctx->act_scale[l + 1 < NLAYER ? l + 1 : l].s[i];
+  }
   P.row_tiles = (int)((P.rows + TN - 1) / TN);
   static const int dbg = getenv("FPS_TC_DEBUG") ? atoi(getenv("FPS_TC_DEBUG")) : 0;
   P.debug = dbg;
-  static const int seg = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : SEG_SLABS;
+  static const int seg_env = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : 0;
+  const int slab_k = f16 ? 2 * TK : TK;
+  const int seg = seg_env ? seg_env : 128 / slab_k;    // K = 128 per tensor-core accumulation segment
   P.seg = seg;
-  // Truncation-bias compensation (see header): the tensor core rounds the fp32 accumulator toward zero
-  // after every MMA, which shrinks a K_seg-long segment sum by kappa(K_seg) on average; measured on B200
-  // against the fp64 oracle (tools/calibrate_kappa.py): 4.2 ulp at K=32, 6 ulp at K=64, 9 ulp at K=128,
-  // i.e. kappa(K) = 4.2 * 2^-23 * (K/32)^0.55.  FPS_TC_KAPPA overrides (calibration runs).
-  auto kappa_of = [](int kseg) { return 4.2f * 1.1920929e-7f * powf((float)kseg / 32.f, 0.55f); };
   static const char* kenv = getenv("FPS_TC_KAPPA");
   const int tail = (P.nk % seg) ? (P.nk % seg) : seg;
-  P.gain = 1.0f + (kenv ? (float)atof(kenv) : kappa_of(seg * TK));
-  P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail * TK));
+  P.gain = 1.0f + (kenv ? (float)atof(kenv) : kappa_of(seg * slab_k, f16));
+  P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail * slab_k, f16));
   const int ncta = s->pair ? 2 : 1;
   const int total = P.row_tiles * (N_FEAT_TILES / ncta);          // tiles of a CTA (pair)
   const int groups_max = ctx->sm_count / ncta;
   const int grid = (total < groups_max ? total : groups_max) * ncta;
-#define FPS_TC_LAUNCH(K_, S_, LAST_) \
-  K_<S_, LAST_><<<grid, TC_THREADS, TC_SMEM, st>>>(s->w_hi[l], s->w_lo[l], s->act_hi[b][kv], s->act_lo[b][kv], P)
+  const CUtensorMap& m1 = f16 ? s->w_hi16[l] : s->w_hi[l];
+  const CUtensorMap& m2 = f16 ? s->w_lo16[l] : s->w_lo[l];
+  const CUtensorMap& m3 = f16 ? s->act_hi16[b][kv] : s->act_hi[b][kv];
+  const CUtensorMap& m4 = f16 ? s->act_lo16[b][kv] : s->act_lo[b][kv];
+#define FPS_TC_LAUNCH(K_, S_, LAST_, F_) K_<S_, LAST_, F_><<<grid, TC_THREADS, TC_SMEM, st>>>(m1, m2, m3, m4, P)
+#define FPS_TC_PICK(K_, F_)                                                                  \
+  do {                                                                                       \
+    if (streams == 4) {                                                                      \
+      if (last) FPS_TC_LAUNCH(K_, 4, true, F_); else FPS_TC_LAUNCH(K_, 4, false, F_);        \
+    } else {                                                                                 \
+      if (last) FPS_TC_LAUNCH(K_, 1, true, F_); else FPS_TC_LAUNCH(K_, 1, false, F_);        \
+    }                                                                                        \
+  } while (0)
   if (s->pair) {
-    if (streams == 4) {
-      if (last) FPS_TC_LAUNCH(layer_tc_pair_kernel, 4, true); else FPS_TC_LAUNCH(layer_tc_pair_kernel, 4, false);
-    } else {
-      if (last) FPS_TC_LAUNCH(layer_tc_pair_kernel, 1, true); else FPS_TC_LAUNCH(layer_tc_pair_kernel, 1, false);
-    }
+    if (f16) FPS_TC_PICK(layer_tc_pair_kernel, true); else FPS_TC_PICK(layer_tc_pair_kernel, false);
   } else {
-    if (streams == 4) {
-      if (last) FPS_TC_LAUNCH(layer_tc_kernel, 4, true); else FPS_TC_LAUNCH(layer_tc_kernel, 4, false);
-    } else {
-      if (last) FPS_TC_LAUNCH(layer_tc_kernel, 1, true); else FPS_TC_LAUNCH(layer_tc_kernel, 1, false);
-    }
+    if (f16) FPS_TC_PICK(layer_tc_kernel, true); else FPS_TC_PICK(layer_tc_kernel, false);
   }
+#undef FPS_TC_PICK
 #undef FPS_TC_LAUNCH
   count_launch();
   FPS_CUDA(cudaGetLastError());
@@ -546,3 +632,12 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
 }
 
 }  // namespace fps
+
+extern "C" int fps_debug_tc_stats(unsigned long long* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, fps::g_tc_stats, sizeof(fps::g_tc_stats)) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    if (cudaMemcpyToSymbol(fps::g_tc_stats, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
