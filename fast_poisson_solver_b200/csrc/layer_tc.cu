@@ -564,8 +564,18 @@ void tc_destroy(fps_ctx* ctx) {
 // K=64, 9 ulp at K=128, i.e. kappa(K) = 4.2 * 2^-23 * (K/32)^0.55.  The TF32 + 2xFP16 scheme issues 2 MMAs
 // per 8 k, so the same law is evaluated at 2/3 of the MMA count.  FPS_TC_KAPPA overrides (calibration).
 static float kappa_of(int kseg, bool f16) {
-  // 3xTF32: 4.2 ulp at K = 32 (48 MMAs per K = 128); FP16x2 split: 3.0e-7 at K = 128 (24 MMAs, calibrated)
-  if (f16) return 3.0e-7f * powf((float)kseg / 128.f, 0.55f);
+  if (f16) {
+    // FP16x2 split, calibrated on B200 against the fp64 oracle (tools/calibrate_kappa.py): optimal gain per
+    // segment length K; piecewise linear in between, proportional below K = 128.
+    static const float K[5] = {128.f, 192.f, 256.f, 352.f, 704.f};
+    static const float V[5] = {3.0e-7f, 5.2e-7f, 7.6e-7f, 1.03e-6f, 2.05e-6f};
+    const float k = (float)kseg;
+    if (k <= K[0]) return V[0] * k / K[0];
+    for (int i = 1; i < 5; ++i)
+      if (k <= K[i]) return V[i - 1] + (V[i] - V[i - 1]) * (k - K[i - 1]) / (K[i] - K[i - 1]);
+    return V[4] * k / K[4];
+  }
+  // 3xTF32: 4.2 ulp at K = 32, 6 ulp at K = 64, 9 ulp at K = 128
   return 4.2f * 1.1920929e-7f * powf((float)kseg / 32.f, 0.55f);
 }
 
@@ -596,7 +606,8 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.debug = dbg;
   static const int seg_env = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : 0;
   const int slab_k = f16 ? 2 * TK : TK;
-  const int seg = seg_env ? seg_env : 128 / slab_k;    // K = 128 per tensor-core accumulation segment
+  // K per tensor-core accumulation segment: 192 (FP16x2: 3 segments + a 128 tail per 704) or 128 (3xTF32)
+  const int seg = seg_env ? seg_env : (f16 ? 192 : 128) / slab_k;
   P.seg = seg;
   static const char* kenv = getenv("FPS_TC_KAPPA");
   const int tail = (P.nk % seg) ? (P.nk % seg) : seg;
