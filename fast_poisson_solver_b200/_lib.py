@@ -43,6 +43,8 @@ SIGNATURES = {
     "fps_destroy": (_i32, [_vp]),
     "fps_set_engine": (_i32, [_vp, _i32]),
     "fps_get_engine": (_i32, [_vp]),
+    "fps_calibrate_scales": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "fps_get_scales": (_i32, [_vp, C.POINTER(C.c_float)]),
     "fps_workspace_bytes": (C.c_size_t, [_vp]),
     "fps_features": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "fps_gram_accum": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),

@@ -110,6 +110,25 @@ static int upload_layer(Layer& L, const float* w, const float* b, int cols, int 
   return 0;
 }
 
+// max |v| per stream (row % S) over a (rows x K) hi/lo fp32 plane pair -> out[4] (atomicMax on float bits)
+template <int S>
+__global__ void plane_absmax_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int64_t rows, int K,
+                                    unsigned int* __restrict__ out) {
+  float m[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    float mm = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) mm = fmaxf(mm, fabsf(hi[r * K + k] + lo[r * K + k]));
+    m[S == 4 ? (int)(r & 3) : 0] = fmaxf(m[S == 4 ? (int)(r & 3) : 0], mm);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    float v = m[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x % 32 == 0 && v > 0.f) atomicMax(out + s, __float_as_uint(v));  // non-negative floats order like uints
+  }
+}
+
 }  // namespace fps
 
 using namespace fps;
@@ -201,6 +220,56 @@ int fps_destroy(fps_ctx* ctx) {
   cudaFree(ctx->partial);
   delete ctx->prof;
   delete ctx;
+  return 0;
+}
+
+// ---- operand-scale calibration for the FP16x2-split planes ----------------------------------------
+int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t n, void* stream) {
+  FPS_REQUIRE(ctx && x && y && n > 0, "fps_calibrate_scales: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t np = n < 1024 ? n : 1024;
+  unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->partial);  // NLAYER x 4 words of scratch
+  FPS_CUDA(cudaMemsetAsync(d_max, 0, NLAYER * 4 * sizeof(unsigned int), st));
+  // run the sample through the fp32 cross-check engine with TF32-format planes and look at every layer input
+  const int f16_saved = ctx->f16;
+  ctx->f16 = 0;
+  for (int i = 0; i < 2; ++i) ctx->act[i].f16 = 0;
+  int cur = 0, rc = launch_fourier(ctx, x, y, np, NSTREAM, ctx->act[cur], st);
+  for (int l = 0; l < NLAYER && rc == 0; ++l) {
+    const int K = ctx->layer[l].Kp;
+    plane_absmax_kernel<4><<<64, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, K, d_max + 4 * l);
+    count_launch();
+    if (l < NLAYER - 1) {
+      rc = launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st);
+      cur ^= 1;
+    }
+  }
+  ctx->f16 = f16_saved;
+  for (int i = 0; i < 2; ++i) ctx->act[i].f16 = f16_saved;
+  if (rc) return rc;
+  unsigned int h_max[NLAYER * 4];
+  FPS_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+  FPS_CUDA(cudaStreamSynchronize(st));
+  for (int l = 0; l < NLAYER; ++l)
+    for (int s = 0; s < 4; ++s) {
+      float m;
+      memcpy(&m, &h_max[4 * l + s], 4);
+      FPS_REQUIRE(m == m && m < 3.0e38f, "fps_calibrate_scales: non-finite activations in layer %d stream %d", l, s);
+      // largest power of two with max * scale <= 64: typical values land near 1..16, and the sample maximum may
+      // be exceeded a thousandfold before fp16 (65504) overflows
+      float sc = 1.0f;
+      if (m > 0.f) sc = exp2f(floorf(log2f(64.0f / m)));
+      if (sc > 1.0e6f) sc = 1.0e6f;
+      if (sc < 1.0e-6f) sc = 1.0e-6f;
+      ctx->act_scale[l].s[s] = sc;
+    }
+  return 0;
+}
+
+int fps_get_scales(const fps_ctx* ctx, float* out24) {
+  FPS_REQUIRE(ctx && out24, "fps_get_scales: null argument");
+  for (int l = 0; l < NLAYER; ++l)
+    for (int s = 0; s < 4; ++s) out24[4 * l + s] = ctx->act_scale[l].s[s];
   return 0;
 }
 

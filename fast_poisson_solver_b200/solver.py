@@ -235,6 +235,10 @@ class Solver:
             if load and os.path.isfile(self.precompute_file):
                 self._load_precomputed()
             else:
+                if self._fdtype == torch.float32 and x64[0].numel():
+                    # fit the fp16 operand scales of the tensor-core engine to this network / domain (1 ms)
+                    _lib.check(self._lib.fps_calibrate_scales(self._ctx, x64[0].data_ptr(), x64[1].data_ptr(),
+                                                              x64[0].numel(), self._stream()), "fps_calibrate_scales")
                 self._Hp, self._DHp = self._features(x64[0], x64[1], True)      # solver.py:162-166
                 self._Hbcp, _ = self._features(x64[2], x64[3], False)           # solver.py:173-175
                 packed = PackedNormal(self._tdev)

@@ -347,3 +347,32 @@ def test_device_sine_sources_and_evaluate(solver_factory):
     assert o.rel_l2(again.cpu().numpy(), u_pde.cpu().numpy()) < 1e-6
     mid = s.evaluate(np.array([0.5, 0.25]), np.array([0.5, 0.75]))
     assert mid.shape == (2, 3) and torch.isfinite(mid).all()
+
+
+def test_fp16_operand_scales_are_calibrated_and_robust(golden, solver_factory):
+    """The tensor-core engine stores layer inputs as scaled fp16 hi/lo planes; precompute calibrates the
+    scales on the actual points.  A weight set with 30x larger derivative streams (scaled Fourier
+    frequencies) must neither overflow nor lose accuracy."""
+    import ctypes as C
+    from fast_poisson_solver_b200 import weights as W
+
+    g = golden("features_seed0.npz")
+    sd = W.default_init(0)
+    s = solver_factory(weights=sd)
+    xp, yp, xb, yb = o.grid_problem(24)
+    s.precompute(xp, yp, xb, yb)
+    sc = (C.c_float * 24)()
+    s._lib.fps_get_scales(s._ctx, sc)
+    sc = np.array(list(sc)).reshape(6, 4)
+    assert np.all(np.log2(sc) == np.round(np.log2(sc)))          # powers of two
+    assert np.all(sc[:, 3] < sc[:, 0])                            # laplacian stream is the largest
+    # stress: 3x the Fourier frequencies -> ~3x / 9x larger d/dx, laplacian streams
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["mapping.freqs"] = sd["mapping.freqs"] * 3.0
+    s2 = solver_factory(weights=sd2)
+    s2.precompute(xp, yp, xb, yb)
+    w2 = {k: v.numpy() for k, v in sd2.items()}
+    Hr, DHr = o.features_forward(xp, yp, w2, np.float64)
+    assert torch.isfinite(s2.DH).all()
+    assert o.rel_l2(s2.H.cpu().numpy(), Hr) < TOL_FEATURE
+    assert o.rel_l2(s2.DH.cpu().numpy(), DHr) < TOL_FEATURE
