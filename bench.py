@@ -387,7 +387,9 @@ def run_ours(args):
                      "launches": int(hid_n), "avg_launch_ms": hid_ms / hid_n if hid_n else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one 18 944-point launch, ncu --set full,
                      # profiles/r01b_layer_tc_ncu_full_summary.csv (algorithmic: 427 MB in + 424 MB out + 4 MB weights)
-                     "traffic": None},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one 18 944-point launch (ncu --set full,
+                     # profiles/r01c_layer_tc_ncu_full_summary.csv); algorithmic: 213 MB in + 212 MB out + 2 MB weights
+                     "traffic": 388.8e6 if f16_fmt else 846.7e6, "traffic_unit": "bytes/launch (ncu)"},
         "other_rooflines": {
             "features_all_layers": {"achieved": n_pts * FLOP_PER_POINT_FEATURES / (feat_ms * 1e-3) / 1e12,
                                     "peak": tc_peak, "unit": "TFLOP/s (algorithmic, 3 MMAs issued per product)"},

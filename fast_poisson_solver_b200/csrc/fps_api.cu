@@ -227,7 +227,7 @@ int fps_destroy(fps_ctx* ctx) {
 int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t n, void* stream) {
   FPS_REQUIRE(ctx && x && y && n > 0, "fps_calibrate_scales: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t np = n < 1024 ? n : 1024;
+  const int64_t np = n < 512 ? n : 512;
   unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->partial);  // NLAYER x 4 words of scratch
   FPS_CUDA(cudaMemsetAsync(d_max, 0, NLAYER * 4 * sizeof(unsigned int), st));
   // run the sample through the fp32 cross-check engine with TF32-format planes and look at every layer input
@@ -237,7 +237,7 @@ int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t
   int cur = 0, rc = launch_fourier(ctx, x, y, np, NSTREAM, ctx->act[cur], st);
   for (int l = 0; l < NLAYER && rc == 0; ++l) {
     const int K = ctx->layer[l].Kp;
-    plane_absmax_kernel<4><<<64, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, K, d_max + 4 * l);
+    plane_absmax_kernel<4><<<512, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, K, d_max + 4 * l);
     count_launch();
     if (l < NLAYER - 1) {
       rc = launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st);

@@ -60,7 +60,7 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
 int fps_destroy(fps_ctx* ctx);
 int fps_set_engine(fps_ctx* ctx, int engine);
 /* The tcgen05 engine stores layer inputs as fp16 hi/lo planes of a power-of-two scaled copy.
- * fps_calibrate_scales runs up to 1024 of the given points through the fp32 cross-check engine, measures
+ * fps_calibrate_scales runs up to 512 of the given points through the fp32 cross-check engine, measures
  * max |v| per layer input and stream (value, d/dx, d/dy, laplacian) and sets every scale to the largest
  * power of two with max * scale <= 64 (1000x headroom below the fp16 maximum).  Synchronises the stream.
  * fps_get_scales copies the 6 x 4 scales out (host float[24]).                                       */
