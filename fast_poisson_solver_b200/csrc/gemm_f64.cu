@@ -24,6 +24,19 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                : "d"(a), "d"(b));
 }
 
+// sm_90+ shape: 16x8x16 per instruction (8x fewer issues than m8n8k4).  Fragments (CUTLASS
+// SM90_16x8x16_F64F64F64F64_TN traits; g = lane / 4, t = lane % 4):
+//   a[v0 + 2 v1] = A[g + 8 v0][t + 4 v1]   (v0 < 2, v1 < 4)      b[v] = B[t + 4 v][g]   (v < 4)
+//   c[v0 + 2 v1] = C[g + 8 v1][2 t + v0]   (v0, v1 < 2)
+__device__ __forceinline__ void dmma16x8x16(double* c, const double* a, const double* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+        "d"(b[2]), "d"(b[3]));
+}
+
 constexpr int GT = 64;         // output tile edge
 constexpr int GK = 32;         // rows (contraction) per step
 constexpr int GS = GT + 4;     // smem row stride in doubles: == 4 (mod 16) -> conflict-free fragment loads
@@ -119,11 +132,13 @@ atb_f64_kernel(const TA* __restrict__ A, int64_t lda, int M, const TB* __restric
   const int wi = warp / 2, wj = warp % 2;
   const int lr = lane / 4, lc = lane % 4;
 
-  double c[4][4][2];
+  double c[2][4][4];  // [m16 tile][n8 tile][fragment]
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c[i][j][v] = 0.0;
 
   TileRegs<TA> ra;
   TileRegs<TB> rb;
@@ -139,26 +154,35 @@ atb_f64_kernel(const TA* __restrict__ A, int64_t lda, int M, const TB* __restric
       load_tile_kn<TB>(rb, B, ldb, k0 + GK, kend, tj * GT, Nc, vecB);
     }
 #pragma unroll
-    for (int kk = 0; kk < GK / 4; ++kk) {
-      double a[4], b[4];
+    for (int kk = 0; kk < GK / 16; ++kk) {
+      double a[2][8], b[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + lc) * GS + wi * 32 + i * 8 + lr];
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[(kk * 4 + lc) * GS + wj * 32 + j * 8 + lr];
+        for (int v1 = 0; v1 < 4; ++v1)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+          for (int v0 = 0; v0 < 2; ++v0)
+            a[i][v0 + 2 * v1] = As[(kk * 16 + lc + 4 * v1) * GS + wi * 32 + i * 16 + lr + 8 * v0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma8x8x4(c[i][j][0], c[i][j][1], a[i], b[j]);
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) b[j][v] = Bs[(kk * 16 + lc + 4 * v) * GS + wj * 32 + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma16x8x16(c[i][j], a[i], b[j]);
     }
   }
   double* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (GT * GT);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = wi * 32 + i * 8 + lr, cc = wj * 32 + j * 8 + lc * 2;
-      *reinterpret_cast<double2*>(out + r * GT + cc) = make_double2(c[i][j][0], c[i][j][1]);
-    }
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int v1 = 0; v1 < 2; ++v1) {
+        const int r = wi * 32 + i * 16 + lr + 8 * v1, cc = wj * 32 + j * 8 + lc * 2;
+        *reinterpret_cast<double2*>(out + r * GT + cc) = make_double2(c[i][j][2 * v1], c[i][j][2 * v1 + 1]);
+      }
 }
 
 // C += sum_slices partial (fixed order), mirrored for symmetric products.

@@ -215,6 +215,11 @@ class Solver:
         t0 = time.perf_counter()
         if name is not None:
             self.precompute_file = os.path.join(self.precompute_path, name + ".pkl")
+        if self.distributed and ".rank" not in os.path.basename(self.precompute_file):
+            # row-sharded state: one file per rank
+            import torch.distributed as dist
+
+            self.precompute_file = self.precompute_file[:-4] + f".rank{dist.get_rank(self.process_group)}.pkl"
         with torch.cuda.device(self._dev_index):
             x64 = [_as_f64_column(v, self._tdev) for v in (x_pde, y_pde, x_bc, y_bc)]
             self._xy64 = x64
@@ -232,7 +237,15 @@ class Solver:
                          "f_pred", "f", "bc"):
                 if hasattr(self, name):
                     setattr(self, name, None)
-            if load and os.path.isfile(self.precompute_file):
+            use_file = bool(load) and os.path.isfile(self.precompute_file)
+            if self.distributed and load:
+                # every rank must take the same branch (the recompute branch contains collectives)
+                import torch.distributed as dist
+
+                flag = torch.tensor([1.0 if use_file else 0.0], device=self._tdev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.process_group)
+                use_file = flag.item() > 0.5
+            if use_file:
                 self._load_precomputed()
             else:
                 if self._fdtype == torch.float32 and x64[0].numel():
