@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libfps_sm100.so")
 
 F = 700
 FP = 704
+LROWS = 736  # FPS_LROWS: factor buffer rows (L + diagonal-block inverses)
 K0 = 400
 NFREQ = 200
 NHIDDEN = 5

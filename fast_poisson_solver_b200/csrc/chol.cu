@@ -173,6 +173,27 @@ __global__ void chol_fixup_kernel(double* __restrict__ L, const double* __restri
   }
 }
 
+// Inverses of the 22 diagonal 32x32 blocks of L, stored in rows 704..735 of the factor buffer (block kb in
+// columns 32 kb .. 32 kb + 31).  The batched solve applies them as small mat-vecs instead of 32 sequential
+// substitution steps; one step of iterative refinement against the block itself keeps the block solve
+// backward stable.  One warp per block, lane j builds column j by forward substitution on e_j.
+__global__ void chol_dinv_kernel(double* __restrict__ L) {
+  __shared__ double D[CB][CB + 1];
+  const int kb = blockIdx.x, k0 = kb * CB, j = threadIdx.x;
+  for (int e = threadIdx.x; e < CB * CB; e += 32) D[e / CB][e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
+  __syncwarp();
+  double x[CB];
+#pragma unroll
+  for (int i = 0; i < CB; ++i) {
+    double sacc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < i; ++m) sacc = fma(-D[i][m], x[m], sacc);
+    x[i] = (i >= j) ? sacc / D[i][i] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < CB; ++i) L[(size_t)(CN + i) * CN + k0 + j] = x[i];
+}
+
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
                            int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,
                            cudaStream_t st) {
@@ -182,7 +203,7 @@ int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gb
   double* scal = ctx->partial;
   double* Dfac = ctx->partial + 8;
   for (int li = 0; li < n_lambda; ++li) {
-    double* Ll = L + (size_t)li * CN * CN;
+    double* Ll = L + (size_t)li * FPS_LROWS * CN;
     const double lam = h_lambdas[li];
     const double jitter = h_jitter ? h_jitter[li] : 0.0;
     assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam / (double)n_total, 1.0 / (double)nbc_total, jitter, Ll);
@@ -197,8 +218,9 @@ int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gb
       }
     }
     chol_fixup_kernel<<<CN, 256, 0, st>>>(Ll, Dfac);
+    chol_dinv_kernel<<<CNB, 32, 0, st>>>(Ll);
   }
-  count_launch(n_lambda * (3 + CNB + (CNB - 1)));
+  count_launch(n_lambda * (4 + CNB + (CNB - 1)));
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -214,8 +236,9 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
                       double* __restrict__ W, double* __restrict__ bias) {
   extern __shared__ double sm[];
   double* X = sm;                  // [CN][SC]
-  double* D = sm + CN * SC;        // [CB][CB+1] diagonal block
-  double* xb = D + CB * (CB + 1);  // [CB][SC] solved block
+  double* D = sm + CN * SC;        // [CB][CB+1] diagonal block (lower triangle, zeros above)
+  double* Di = D + CB * (CB + 1);  // [CB][CB+1] its inverse
+  double* xb = Di + CB * (CB + 1); // [CB][SC] solved block
   const int t = threadIdx.x, warp = t / 32, lane = t % 32;
   const int c0 = blockIdx.x * SC;
   for (int e = t; e < CN * SC; e += 256) {
@@ -226,16 +249,23 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
   for (int kb = 0; kb < CNB; ++kb) {
     const int k0 = kb * CB;
     __syncthreads();
-    for (int e = t; e < CB * CB; e += 256) D[(e / CB) * (CB + 1) + e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
+    for (int e = t; e < CB * CB; e += 256) {
+      const int i = e / CB, j = e % CB;
+      D[i * (CB + 1) + j] = (j <= i) ? L[(size_t)(k0 + i) * CN + k0 + j] : 0.0;
+      Di[i * (CB + 1) + j] = L[(size_t)(CN + i) * CN + k0 + j];
+    }
     __syncthreads();
     {
-      double x = X[(k0 + lane) * SC + warp];
-#pragma unroll 4
-      for (int j = 0; j < CB; ++j) {
-        double xj = __shfl_sync(0xffffffffu, x, j) / D[j * (CB + 1) + j];
-        if (lane == j) x = xj;
-        else if (lane > j) x = fma(-D[lane * (CB + 1) + j], xj, x);
-      }
+      // x = Dinv b, then one refinement step x += Dinv (b - D x); lane = row, warp = right-hand side
+      const double b = X[(k0 + lane) * SC + warp];
+      double x = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < CB; ++j) x = fma(Di[lane * (CB + 1) + j], __shfl_sync(0xffffffffu, b, j), x);
+      double r = b;
+#pragma unroll 8
+      for (int j = 0; j < CB; ++j) r = fma(-D[lane * (CB + 1) + j], __shfl_sync(0xffffffffu, x, j), r);
+#pragma unroll 8
+      for (int j = 0; j < CB; ++j) x = fma(Di[lane * (CB + 1) + j], __shfl_sync(0xffffffffu, r, j), x);
       X[(k0 + lane) * SC + warp] = x;
       xb[lane * SC + warp] = x;
     }
@@ -259,16 +289,23 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
   for (int kb = CNB - 1; kb >= 0; --kb) {
     const int k0 = kb * CB;
     __syncthreads();
-    for (int e = t; e < CB * CB; e += 256) D[(e / CB) * (CB + 1) + e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
+    for (int e = t; e < CB * CB; e += 256) {
+      const int i = e / CB, j = e % CB;
+      D[i * (CB + 1) + j] = (j <= i) ? L[(size_t)(k0 + i) * CN + k0 + j] : 0.0;
+      Di[i * (CB + 1) + j] = L[(size_t)(CN + i) * CN + k0 + j];
+    }
     __syncthreads();
     {
-      double x = X[(k0 + lane) * SC + warp];
-#pragma unroll 4
-      for (int j = CB - 1; j >= 0; --j) {
-        double xj = __shfl_sync(0xffffffffu, x, j) / D[j * (CB + 1) + j];
-        if (lane == j) x = xj;
-        else if (lane < j) x = fma(-D[j * (CB + 1) + lane], xj, x);  // (L^T)[lane][j] = L[j][lane]
-      }
+      // transposed block: x = Dinv^T b, refined against D^T
+      const double b = X[(k0 + lane) * SC + warp];
+      double x = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < CB; ++j) x = fma(Di[j * (CB + 1) + lane], __shfl_sync(0xffffffffu, b, j), x);
+      double r = b;
+#pragma unroll 8
+      for (int j = 0; j < CB; ++j) r = fma(-D[j * (CB + 1) + lane], __shfl_sync(0xffffffffu, x, j), r);
+#pragma unroll 8
+      for (int j = 0; j < CB; ++j) x = fma(Di[j * (CB + 1) + lane], __shfl_sync(0xffffffffu, r, j), x);
       X[(k0 + lane) * SC + warp] = x;
       xb[lane * SC + warp] = x;
     }
@@ -306,7 +343,7 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
 int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
                           const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st) {
   if (B <= 0) return 0;
-  const size_t smem = (size_t)(CN * SC + CB * (CB + 1) + CB * SC) * sizeof(double);
+  const size_t smem = (size_t)(CN * SC + 2 * CB * (CB + 1) + CB * SC) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     FPS_CUDA(cudaFuncSetAttribute(solve_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -225,8 +225,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 
 // FPS_TC_DEBUG=9: cycle accounting of CTA 0 (developer instrumentation, read with fps_debug_tc_stats)
-__device__ unsigned long long g_tc_stats[8];
-#define TC_STAT_ADD(i, v) do { if (P.debug == 9 && blockIdx.x == 0) atomicAdd(&g_tc_stats[i], (unsigned long long)(v)); } while (0)
+__device__ unsigned long long g_tc_stats[16];
+#define TC_STAT_ADD(i, v) do { if (P.stats && blockIdx.x == 0) atomicAdd(&g_tc_stats[i], (unsigned long long)(v)); } while (0)
 
 struct TcParams {
   const float* bias;
@@ -238,6 +238,7 @@ struct TcParams {
   int nk;         // K slabs of TK
   int row_tiles;  // ceil(rows / 256)
   int debug;      // FPS_TC_DEBUG experiments (0 = production)
+  int stats;      // FPS_TC_STATS=1: cycle accounting of CTA 0 into g_tc_stats
   int seg;        // K slabs per tensor-core accumulation segment
   float in_inv[4]; // per stream: 1 / (W16_SCALE * input scale) (FP16x2 format), else 1
   float out_sc[4]; // per stream: scale of the next layer's input planes
@@ -312,7 +313,9 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
         const int ft = (t % FT_GROUPS) * NCTA + rank, rt = t / FT_GROUPS;
         const int brow = rt * TN + rank * (TN / NCTA);
         for (int kc = 0; kc < P.nk; ++kc) {
+          const long long t_p = clock64();
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          TC_STAT_ADD(7, clock64() - t_p);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
           if (rank == 0) mbar_expect_tx(full, STAGE_BYTES * NCTA);
@@ -345,6 +348,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
             const long long t_b = clock64();
             mbar_wait(bar_full + 8 * stage, phase);
             TC_STAT_ADD(0, clock64() - t_b);
+            if (kc == 0) TC_STAT_ADD(8, clock64() - t_b);   // first slab of a tile
             tc_fence_after();
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), a_lo = umma_desc<ROW_BYTES>(sa + BOX_BYTES);
@@ -397,7 +401,6 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
 #pragma unroll
         for (int c = 0; c < TN / 64; ++c) {
           float v[32];
-          if (P.debug == 2 && c > 0) continue;
           tmem_ld32(taddr + c * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(v[i], g, acc[c * 32 + i]);  // RN promotion + bias gain
@@ -422,7 +425,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           float h, hx, hy, hl;
           tanh_streams(fmaf(acc[4 * q], P.in_inv[0], bias), acc[4 * q + 1] * P.in_inv[1], acc[4 * q + 2] * P.in_inv[2],
                        acc[4 * q + 3] * P.in_inv[3], h, hx, hy, hl);
-          if (f_ok && r < P.rows && !(P.debug == 4 && h != 123.456f)) {
+          if (f_ok && r < P.rows) {
             if (LAST) {
               const int64_t p = r >> 2;
               P.H[p * P.ld + f] = h;
@@ -604,6 +607,8 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.row_tiles = (int)((P.rows + TN - 1) / TN);
   static const int dbg = getenv("FPS_TC_DEBUG") ? atoi(getenv("FPS_TC_DEBUG")) : 0;
   P.debug = dbg;
+  static const int stats = getenv("FPS_TC_STATS") ? atoi(getenv("FPS_TC_STATS")) : 0;
+  P.stats = stats;
   static const int seg_env = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : 0;
   const int slab_k = f16 ? 2 * TK : TK;
   // K per tensor-core accumulation segment: 192 (FP16x2: 3 segments + a 128 tail per 704) or 128 (3xTF32)
@@ -644,10 +649,10 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
 
 }  // namespace fps
 
-extern "C" int fps_debug_tc_stats(unsigned long long* out8, int reset) {
-  if (cudaMemcpyFromSymbol(out8, fps::g_tc_stats, sizeof(fps::g_tc_stats)) != cudaSuccess) return 1;
+extern "C" int fps_debug_tc_stats(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, fps::g_tc_stats, sizeof(fps::g_tc_stats)) != cudaSuccess) return 1;
   if (reset) {
-    unsigned long long z[8] = {0};
+    unsigned long long z[16] = {0};
     if (cudaMemcpyToSymbol(fps::g_tc_stats, z, sizeof(z)) != cudaSuccess) return 1;
   }
   return 0;

@@ -186,7 +186,7 @@ class Solver:
 
         nl = self.n_lambdas
         lam = (C.c_double * nl)(*[float(l) for l in self.lambdas_pde])
-        self._L64 = torch.empty((nl, FP, FP), dtype=torch.float64, device=self._tdev)
+        self._L64 = torch.empty((nl, _lib.LROWS, FP), dtype=torch.float64, device=self._tdev)
         info = torch.zeros(nl, dtype=torch.int32, device=self._tdev)
         diag_scale = [float(l) / self.NO * float(self._G64.diagonal()[:F].max()) +
                       float(self._Gbc64.diagonal()[:F].max()) / self.NdO for l in self.lambdas_pde]
@@ -311,7 +311,7 @@ class Solver:
     # ---- precomputed-state persistence (solver.py:180-185, :201-207) ------------------------------
     def _save_precomputed(self):
         payload = {
-            "format": "fps_b200/1",
+            "format": "fps_b200/2",
             "H": self._Hp.cpu(), "DH": self._DHp.cpu(), "H_bc": self._Hbcp.cpu(), "pack": self._pack.cpu(),
             "L64": self._L64.cpu(), "NO": self.NO, "NdO": self.NdO, "lambdas": self.lambdas_pde, "jitter": self.jitter,
         }
@@ -323,7 +323,7 @@ class Solver:
     def _load_precomputed(self):
         with open(self.precompute_file, "rb") as fh:
             p = pickle.load(fh)
-        if not isinstance(p, dict) or p.get("format") != "fps_b200/1":
+        if not isinstance(p, dict) or p.get("format") != "fps_b200/2":
             raise _lib.FpsError(f"{self.precompute_file} was not written by this implementation")
         self._Hp, self._DHp, self._Hbcp = (p[k].to(self._tdev) for k in ("H", "DH", "H_bc"))
         pack = p["pack"].to(self._tdev)

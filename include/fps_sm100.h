@@ -31,6 +31,7 @@ extern "C" {
 #define FPS_FP 704       /* FPS_F padded to a multiple of 64                                  */
 #define FPS_K0 400       /* 2 * ffm.num Fourier inputs, resources/infos.yaml:843-848          */
 #define FPS_NFREQ 200
+#define FPS_LROWS 736    /* rows of one Cholesky factor buffer: 704 of L + 32 of diagonal-block inverses */
 #define FPS_NHIDDEN 5    /* depth-1 Linear(700,700)+Tanh blocks, model.py:49-60               */
 
 #define FPS_ENGINE_SIMT 0     /* fp32 FFMA layer kernel (bring-up / cross-check engine)        */
@@ -87,8 +88,9 @@ int fps_colsum_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double
 /* Replaces precompute_LHS_RHS (solver.py:187-199) and the LU inside torch.linalg.solve
  * (solver.py:305):  for every lambda
  *     LHS = lambda/N * G + ( Gbc - s s^T / N_bc ) / N_bc          (centering matrix folded in)
- * then the in-place lower Cholesky factor L of LHS is left in L64[(i), :, :] (n_lambda, FPS_FP,
- * FPS_FP) float64 (mirrored into the upper triangle).  h_lambdas / h_jitter are HOST arrays of
+ * then the lower Cholesky factor L of LHS is left in L64[(i), :FPS_FP, :] of the (n_lambda, FPS_LROWS,
+ * FPS_FP) float64 buffer (mirrored into the upper triangle); rows FPS_FP.. hold the inverses of the 22
+ * diagonal 32x32 blocks that fps_solve_factored applies.  h_lambdas / h_jitter are HOST arrays of
  * n_lambda entries; h_jitter (may be NULL = 0) is an absolute diagonal shift added to LHS - the
  * matrix has cond ~1e15 and is exactly singular when N + N_bc < 700, so the caller starts at 0 and
  * raises the shift only when info reports a breakdown.  info (device int[n_lambda]) receives 0 or
@@ -105,7 +107,8 @@ int fps_project_rhs(fps_ctx* ctx, const float* DH, int64_t n, int64_t ld, const 
 
 /* Replaces torch.linalg.solve + the bias formula (solver.py:305-306) for B right-hand sides:
  *     W = (L L^T)^-1 (scale * R),   bias_j = -( s^T W_j - sum_bc_j ) / N_bc
- * R64 (FPS_FP, ldr) float64 in, W64 (FPS_FP, ldr) float64 out (may alias R64), sum_bc64 (B),
+ * L64 = one (FPS_LROWS, FPS_FP) factor buffer; R64 (FPS_FP, ldr) float64 in, W64 (FPS_FP, ldr) float64 out
+ * (may alias R64), sum_bc64 (B),
  * bias64 (B).  scale = lambda / N.                                                             */
 int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64_t ldr, int B,
                        double scale, const double* s64, const double* sum_bc64, int64_t nbc_total,
