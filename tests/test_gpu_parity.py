@@ -376,3 +376,41 @@ def test_fp16_operand_scales_are_calibrated_and_robust(golden, solver_factory):
     assert torch.isfinite(s2.DH).all()
     assert o.rel_l2(s2.H.cpu().numpy(), Hr) < TOL_FEATURE
     assert o.rel_l2(s2.DH.cpu().numpy(), DHr) < TOL_FEATURE
+
+
+def test_full_size_properties_config2(solver_factory):
+    """BASELINE configs[1] size (2^20 scattered points): size-independent properties instead of an oracle run.
+    linearity of solve in (f, bc), batch == single, evaluate() == u_pde at the collocation points,
+    tensor-core engine == fp32 cross-check engine on a sub-sample, residual of the fitted source."""
+    from scipy.stats import qmc
+
+    n = 1 << 20
+    pts = qmc.Sobol(d=2, scramble=True, seed=0).random(n)
+    x = torch.tensor(pts[:, 0], device="cuda")
+    y = torch.tensor(pts[:, 1], device="cuda")
+    g = np.linspace(0, 1, 1026)
+    xb = np.concatenate([g, g, np.zeros(1024), np.ones(1024)])
+    yb = np.concatenate([np.zeros(1026), np.ones(1026), g[1:-1], g[1:-1]])
+    s = solver_factory()
+    s.precompute(x, y, xb, yb)
+    assert s.NO == n and s.NdO == 4100 and s.H.shape == (n, 700) and s.jitter == [0.0]
+    f1 = 30.0 * torch.sin(2 * np.pi * x) * torch.sin(3 * np.pi * y)
+    f2 = 20.0 * torch.cos(np.pi * x) * y
+    F = torch.stack([f1, f2, 2.0 * f1 - 0.5 * f2], dim=1).float()
+    bcv = np.array([1.0, -2.0, 2.0 * 1.0 - 0.5 * -2.0])
+    u, u_pde, u_bc, f_pred, _ = s.solve(F, bcv)
+    assert u.shape == (n + 4100, 3) and torch.isfinite(u).all()
+    lin = 2.0 * u[:, 0] - 0.5 * u[:, 1]
+    assert (lin - u[:, 2]).norm() / u[:, 2].norm() < 2e-5           # linearity (fp32 outputs)
+    sub = torch.arange(0, n, 997, device="cuda")
+    ue = s.evaluate(x[sub], y[sub])                                   # uses the weights of the last solve
+    assert ue.shape == (sub.numel(), 3)
+    assert (ue - u_pde[sub]).norm() / u_pde[sub].norm() < 1e-5       # u(x, y) re-evaluated
+    u1 = s.solve(F[:, 1], np.full(4100, -2.0))[0]
+    assert (u1[:, 0] - u[:, 1]).norm() / u[:, 1].norm() < 1e-6       # batched == single
+    assert (f_pred[:, 0] - F[:, 0]).norm() / F[:, 0].norm() < 1e-2   # the fitted source
+    assert (u_bc[:, 0] - 1.0).abs().max() < 1e-2
+    ref = solver_factory(engine="simt")
+    Hs, DHs = ref._features(x[sub].double(), y[sub].double(), True)
+    assert o.rel_l2(s.DH[sub].cpu().numpy(), DHs[:, :700].cpu().numpy()) < 3e-6
+    assert o.rel_l2(s.H[sub].cpu().numpy(), Hs[:, :700].cpu().numpy()) < 3e-6
