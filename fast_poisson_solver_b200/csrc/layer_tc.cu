@@ -376,6 +376,12 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
         }
       }
       TC_STAT_ADD(2, clock64() - t_loop);
+      if (P.stats) {  // all pair leaders: sum / max / count of the per-launch MMA loop time
+        const unsigned long long dt = (unsigned long long)(clock64() - t_loop);
+        atomicAdd(&g_tc_stats[9], dt);
+        atomicMax(&g_tc_stats[10], dt);
+        atomicAdd(&g_tc_stats[11], 1ull);
+      }
     }
   } else {
     // ================= accumulate + epilogue (warps 2..9) =================

@@ -39,3 +39,4 @@ if os.environ.get("FPS_TC_STATS") == "1":
     v = list(buf)
     tiles = max(1, v[6])
     print({n: round(x / tiles) for n, x in zip(names, v) if n not in ("tiles", "-")}, "cycles per tile over", v[6], "tiles (CTA 0, all layers)")
+    print("all leaders: mean loop cycles per launch %.0f, max %d, n %d" % (v[9] / max(1, v[11]), v[10], v[11]))
