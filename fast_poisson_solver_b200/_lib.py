@@ -66,6 +66,7 @@ SIGNATURES = {
     "fps_profile_enable": (_i32, [_vp, _i32]),
     "fps_profile_reset": (_i32, [_vp]),
     "fps_profile_read": (_i32, [_vp, _i32, C.POINTER(_f64), C.POINTER(_i64)]),
+    "fps_debug_tc_stats": (_i32, [_vp, _i32]),
 }
 PROF_KINDS = ["fourier", "layer0", "hidden", "last", "gram", "factor", "project", "trisolve", "reconstruct"]
 

@@ -224,7 +224,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 
-// FPS_TC_DEBUG=9: cycle accounting of CTA 0 (developer instrumentation, read with fps_debug_tc_stats)
+// FPS_TC_STATS=1: in-kernel cycle accounting (developer instrumentation, read with fps_debug_tc_stats)
 __device__ unsigned long long g_tc_stats[16];
 #define TC_STAT_ADD(i, v) do { if (P.stats && blockIdx.x == 0) atomicAdd(&g_tc_stats[i], (unsigned long long)(v)); } while (0)
 
@@ -237,7 +237,6 @@ struct TcParams {
   int64_t rows;   // valid activation rows = points * S
   int nk;         // K slabs of TK
   int row_tiles;  // ceil(rows / 256)
-  int debug;      // FPS_TC_DEBUG experiments (0 = production)
   int stats;      // FPS_TC_STATS=1: cycle accounting of CTA 0 into g_tc_stats
   int seg;        // K slabs per tensor-core accumulation segment
   float in_inv[4]; // per stream: 1 / (W16_SCALE * input scale) (FP16x2 format), else 1
@@ -611,8 +610,6 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
     P.out_sc[i] = ctx->act_scale[l + 1 < NLAYER ? l + 1 : l].s[i];
   }
   P.row_tiles = (int)((P.rows + TN - 1) / TN);
-  static const int dbg = getenv("FPS_TC_DEBUG") ? atoi(getenv("FPS_TC_DEBUG")) : 0;
-  P.debug = dbg;
   static const int stats = getenv("FPS_TC_STATS") ? atoi(getenv("FPS_TC_STATS")) : 0;
   P.stats = stats;
   static const int seg_env = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : 0;

@@ -164,6 +164,10 @@ int64_t fps_launch_count(void);
 int fps_profile_enable(fps_ctx* ctx, int on);
 int fps_profile_reset(fps_ctx* ctx);
 int fps_profile_read(fps_ctx* ctx, int kind, double* ms, int64_t* launches);
+/* With FPS_TC_STATS=1 in the environment the tcgen05 layer kernel accumulates SM-clock cycle counters
+ * (operand waits, TMEM waits, promotion, epilogue, per-launch loop time); this copies the 16 counters
+ * to the host array and optionally clears them.  Developer instrumentation (tools/time_features.py).   */
+int fps_debug_tc_stats(unsigned long long* h_out16, int reset);
 
 #ifdef __cplusplus
 }
