@@ -57,6 +57,14 @@ def ring(G):
             np.concatenate([np.zeros_like(g), np.ones_like(g), yg, yg]))
 
 
+def grid_points(G):
+    """Interior G x G grid + boundary ring in the layout of the reference's generator (data.py:192-217)."""
+    g = np.linspace(0.0, 1.0, G + 2)
+    xi, yi = np.meshgrid(g[1:-1], g[1:-1])
+    xb, yb = ring(G)
+    return xi.flatten(), yi.flatten(), xb, yb
+
+
 def perlin(x, y, seed=0, layers=3):
     """Vectorised gradient noise, statistically like source_functions.py:173-227 (1-5 octave layers,
     octaves ~ U(0.1,12), amplitude ~ U(-100,100)); values need not match the absent perlin_noise
@@ -304,9 +312,7 @@ def run_ours(args):
     # ---- batched solve (configs[2]): 512x512 grid, B right-hand sides ---------------------------
     batched = None
     if args.batch > 0:
-        from oracle.fps_oracle import grid_problem
-
-        gx, gy, gxb, gyb = grid_problem(512)
+        gx, gy, gxb, gyb = grid_points(512)
         solver.precompute(d(gx, torch.float64), d(gy, torch.float64), d(gxb, torch.float64), d(gyb, torch.float64))
         B = args.batch
         gen = torch.Generator(device=dev).manual_seed(rank)

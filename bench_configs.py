@@ -81,7 +81,7 @@ def main():
     from fast_poisson_solver_b200 import Solver
     from fast_poisson_solver_b200.parallel import shard_bounds
     from fast_poisson_solver_b200.sources import sine_params, sine_sources, sine_sources_numpy
-    from oracle import fps_oracle as o
+    from bench import grid_points
 
     os.makedirs("/tmp/fps_bench_cwd", exist_ok=True)
     os.chdir("/tmp/fps_bench_cwd")
@@ -108,7 +108,7 @@ def main():
         x, y, xb, yb = domain_points(a.domain, a.points)
         N, Nb = x.size, xb.size
     else:
-        x, y, xb, yb = o.grid_problem(a.grid)
+        x, y, xb, yb = grid_points(a.grid)
         N, Nb = x.size, xb.size
     lo, hi = shard_bounds(N, rank, world)
     blo, bhi = shard_bounds(Nb, rank, world)
@@ -164,10 +164,11 @@ def main():
         Fm = sine_sources(s, par[:ncheck], out=Fbuf[:, :ncheck])
         s.solve(Fm, torch.as_tensor(bcv[:ncheck], device=dev))
         if rank == 0:
-            from oracle import fd_oracle
+            # checker leg: the oracle (test infrastructure) is imported only here, to judge accuracy
+            from oracle import fd_oracle, fps_oracle as o
 
             G = a.fd_grid
-            gx, gy, _, _ = o.grid_problem(G)
+            gx, gy, _, _ = grid_points(G)
             u_ml = s.evaluate(d(gx), d(gy)).double().cpu().numpy()
             u_fd = fd_oracle.fd_solve_dst(G, sine_sources_numpy(gx, gy, par[:ncheck]), bcv[:ncheck])
             out["accuracy_vs_fd"] = {"fd_grid": G, "columns": [dict(o.metrics(u_ml[:, j], u_fd[:, j]),

@@ -414,3 +414,22 @@ def test_full_size_properties_config2(solver_factory):
     Hs, DHs = ref._features(x[sub].double(), y[sub].double(), True)
     assert o.rel_l2(s.DH[sub].cpu().numpy(), DHs[:, :700].cpu().numpy()) < 3e-6
     assert o.rel_l2(s.H[sub].cpu().numpy(), Hs[:, :700].cpu().numpy()) < 3e-6
+
+
+def test_constructor_variants_like_reference_test_solverclass(solver_factory):
+    """tests/test_solverclass.py:46-88 of the reference: ctor variants and the attributes it asserts."""
+    from fast_poisson_solver_b200 import Solver
+
+    s = solver_factory()
+    assert isinstance(s, Solver) and s.device == "cuda" and s.precision == torch.float32
+    assert s.lambdas_pde == [2 ** -12] and s.n_lambdas == 1 and os.path.isdir(s.precompute_path)
+    s = solver_factory(device=torch.device("cuda"))
+    assert s.device == torch.device("cuda")
+    s = solver_factory(device="cuda:0", precision=torch.float64, verbose=True, compile_model=False, seed=3)
+    assert s.precision == torch.float64 and s.device == "cuda:0" and s.compile_model is False
+    with pytest.raises(RuntimeError, match="only CUDA"):
+        Solver(device="cpu", use_weights=False)
+    with pytest.raises(FileNotFoundError):
+        Solver()  # use_weights=True and no final.pt shipped (reference: solver.py:97-99)
+    with pytest.raises(RuntimeError, match="precompute"):
+        solver_factory().solve([0.0], [0.0])
