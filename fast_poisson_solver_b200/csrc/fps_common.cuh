@@ -163,6 +163,20 @@ __device__ __forceinline__ void store_planes(const ActPlanes& P, size_t idx, flo
     P.lo[idx] = v - h;
   }
 }
+// same with the format known at compile time (tensor-core epilogue)
+template <bool F16>
+__device__ __forceinline__ void store_planes_t(const ActPlanes& P, size_t idx, float v, float scale) {
+  if (F16) {
+    const float t = v * scale;
+    const __half h = __float2half_rn(t);
+    P.hi16[idx] = h;
+    P.lo16[idx] = __float2half_rn(t - __half2float(h));
+  } else {
+    const float h = tf32_hi(v);
+    P.hi[idx] = h;
+    P.lo[idx] = v - h;
+  }
+}
 // read it back (SIMT cross-check engine)
 __device__ __forceinline__ float load_planes(const ActPlanes& P, size_t idx, float inv_scale) {
   if (P.f16) return (__half2float(P.hi16[idx]) + __half2float(P.lo16[idx])) * inv_scale;

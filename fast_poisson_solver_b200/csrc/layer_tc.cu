@@ -46,14 +46,13 @@ namespace fps {
 
 constexpr int TM = 128;                 // features per CTA tile (UMMA M per CTA)
 constexpr int TN = 256;                 // activation rows per tile (UMMA N)
-constexpr int TK = 16;                  // fp32 per K slab: 64-byte swizzled rows
-constexpr int ROW_BYTES = TK * 4;       // shared-memory row = swizzle span (SWIZZLE_64B)
-constexpr int BOX_ROWS = 128;           // every TMA box is 128 rows x TK
-constexpr int BOX_BYTES = BOX_ROWS * ROW_BYTES;  // 8 KiB
+constexpr int BOX_ROWS = 128;           // every TMA box is 128 rows x one swizzle span of K
+// The shared-memory row (= swizzle span = K bytes per slab) is a template parameter RB: 64 (SWIZZLE_64B,
+// 8 KiB boxes, 6-stage ring) or 128 (SWIZZLE_128B, 16 KiB boxes, full 128-byte L2 lines per TMA row).
 constexpr int TC_THREADS = 320;         // TMA warp, MMA warp, 8 accumulate/epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int N_FEAT_TILES = FPW / TM;  // 6
-constexpr int RING_BYTES = 192 * 1024;
+constexpr int RING_BYTES = 224 * 1024;
 constexpr int TC_SMEM = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int MAX_STAGES = 8;
 
@@ -243,20 +242,23 @@ struct TcParams {
   float out_sc[4]; // per stream: scale of the next layer's input planes
   float gain;      // 1 + kappa(K_seg): first-order compensation of the accumulator truncation bias
   float gain_tail; // same for the shorter last segment of a tile
+  int stages;      // ring depth actually used (<= RING_BYTES / stage bytes)
 };
 
 // F16 = false: 3xTF32, planes hi32 / lo32, K slab = 16 floats.  F16 = true: FP16x2 split, planes hi16 / lo16,
 // K slab = 32 halves.  Either way a slab row is 64 bytes (SWIZZLE_64B), a box is 128 rows = 8 KiB, one MMA
 // covers 32 bytes of K, and the stage is {Ahi, Alo, Bhi.., Blo..}; only the tensor maps' element type, the
 // MMA kind and the K extent per slab differ.
-template <int S, bool LAST, int NCTA, bool F16>
+template <int S, bool LAST, int NCTA, bool F16, int RB>
 __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CUtensorMap& tmWlo,
                                               const CUtensorMap& tmAhi, const CUtensorMap& tmAlo, const TcParams& P) {
+  constexpr int ROW_BYTES = RB;
+  constexpr int BOX_BYTES = BOX_ROWS * RB;
   constexpr int B_BOXES = TN / BOX_ROWS / NCTA;                   // activation boxes this CTA loads per plane
   constexpr int STAGE_BYTES = 2 * BOX_BYTES + 2 * B_BOXES * BOX_BYTES;  // {Ahi, Alo, Bhi.., Blo..}
-  constexpr int TKE = F16 ? 2 * TK : TK;                          // K elements per slab
-  constexpr int STAGES = RING_BYTES / STAGE_BYTES;                // 4 (single CTA) or 6 (pair)
-  static_assert(STAGES <= MAX_STAGES, "ring too deep for the barrier block");
+  constexpr int TKE = RB / (F16 ? 2 : 4);                         // K elements per slab
+  static_assert(RING_BYTES / STAGE_BYTES <= MAX_STAGES, "ring too deep for the barrier block");
+  const int STAGES = P.stages;                                    // <= RING_BYTES / STAGE_BYTES
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -278,7 +280,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAlo)) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
@@ -423,33 +425,36 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
       // (a shared-memory staged variant with cp.async.bulk stores was measured SLOWER: 29.5 vs 25.1 ms)
       const int64_t r0 = (int64_t)rt * TN + half * (TN / 2);
       const bool f_ok = f < FP;  // features 704..767 are tile padding
-      if (S == 4) {
+      // rows of a point are valid together (rows = points * S), so one test per point suffices; tiles that lie
+      // entirely inside the wave (all but the last row tile) skip the test
+      const bool tile_full = r0 + TN / 2 <= P.rows;
+      const size_t o0 = (size_t)r0 * FP + f;   // element offset of (row r0, feature f) in the output planes
+      if (f_ok) {
+        if (S == 4) {
 #pragma unroll
-        for (int q = 0; q < TN / 8; ++q) {
-          const int64_t r = r0 + q * 4;
-          float h, hx, hy, hl;
-          tanh_streams(fmaf(acc[4 * q], P.in_inv[0], bias), acc[4 * q + 1] * P.in_inv[1], acc[4 * q + 2] * P.in_inv[2],
-                       acc[4 * q + 3] * P.in_inv[3], h, hx, hy, hl);
-          if (f_ok && r < P.rows) {
-            if (LAST) {
-              const int64_t p = r >> 2;
-              P.H[p * P.ld + f] = h;
-              P.DH[p * P.ld + f] = hl;
-            } else {
-              const float o[4] = {h, hx, hy, hl};
+          for (int q = 0; q < TN / 8; ++q) {
+            float o[4];
+            tanh_streams(fmaf(acc[4 * q], P.in_inv[0], bias), acc[4 * q + 1] * P.in_inv[1],
+                         acc[4 * q + 2] * P.in_inv[2], acc[4 * q + 3] * P.in_inv[3], o[0], o[1], o[2], o[3]);
+            if (tile_full || r0 + q * 4 < P.rows) {
+              if (LAST) {
+                const int64_t p = (r0 >> 2) + q;
+                P.H[p * P.ld + f] = o[0];
+                P.DH[p * P.ld + f] = o[3];
+              } else {
 #pragma unroll
-              for (int s = 0; s < 4; ++s) store_planes(P.out, (size_t)(r + s) * FP + f, o[s], P.out_sc[s]);
+                for (int s = 0; s < 4; ++s) store_planes_t<F16>(P.out, o0 + (size_t)(q * 4 + s) * FP, o[s], P.out_sc[s]);
+              }
             }
           }
-        }
-      } else {
+        } else {
 #pragma unroll
-        for (int q = 0; q < TN / 2; ++q) {
-          const int64_t r = r0 + q;
-          const float h = tanhf(fmaf(acc[q], P.in_inv[0], bias));
-          if (f_ok && r < P.rows) {
-            if (LAST) P.H[r * P.ld + f] = h;
-            else store_planes(P.out, (size_t)r * FP + f, h, P.out_sc[0]);
+          for (int q = 0; q < TN / 2; ++q) {
+            const float h = tanhf(fmaf(acc[q], P.in_inv[0], bias));
+            if (tile_full || r0 + q < P.rows) {
+              if (LAST) P.H[(r0 + q) * P.ld + f] = h;
+              else store_planes_t<F16>(P.out, o0 + (size_t)q * FP, h, P.out_sc[0]);
+            }
           }
         }
       }
@@ -469,20 +474,20 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
   }
 }
 
-template <int S, bool LAST, bool F16>
+template <int S, bool LAST, bool F16, int RB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 layer_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                 const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                 const TcParams P) {
-  layer_tc_body<S, LAST, 1, F16>(tmWhi, tmWlo, tmAhi, tmAlo, P);
+  layer_tc_body<S, LAST, 1, F16, RB>(tmWhi, tmWlo, tmAhi, tmAlo, P);
 }
 
-template <int S, bool LAST, bool F16>
+template <int S, bool LAST, bool F16, int RB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 layer_tc_pair_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                      const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                      const TcParams P) {
-  layer_tc_body<S, LAST, 2, F16>(tmWhi, tmWlo, tmAhi, tmAlo, P);
+  layer_tc_body<S, LAST, 2, F16, RB>(tmWhi, tmWlo, tmAhi, tmAlo, P);
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------------------
@@ -493,20 +498,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TcState {
   CUtensorMap w_hi[NLAYER], w_lo[NLAYER], w_hi16[NLAYER], w_lo16[NLAYER];
   CUtensorMap act_hi[2][2], act_lo[2][2], act_hi16[2][2], act_lo16[2][2];  // [buffer][0: K = K0P, 1: K = FP]
+  // 128-byte-row (SWIZZLE_128B) maps of the fp16 planes
+  CUtensorMap w_hi16w[NLAYER], w_lo16w[NLAYER], act_hi16w[2][2], act_lo16w[2][2];
   int pair;
+  int rb;  // shared-memory row bytes of the production (pair, FP16x2) kernel: 64 or 128
 };
 
-// 2-D K-major map: dims {K, rows}, box {64 bytes of K, 128 rows}, SWIZZLE_64B (16 floats or 32 halves per row)
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, bool half) {
+// 2-D K-major map: dims {K, rows}, box {rb bytes of K, 128 rows}, swizzle span = rb (64: 16 floats or 32 halves
+// per row; 128: 64 halves per row).  A box that overhangs K (K0P = 416 with 64-wide slabs) is zero-filled.
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, bool half,
+                    int rb = 64) {
   const uint64_t esz = half ? 2 : 4;
   cuuint64_t dims[2] = {K, rows};
   cuuint64_t strides[1] = {K * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)BOX_ROWS};
+  cuuint32_t box[2] = {(cuuint32_t)(rb / esz), (cuuint32_t)BOX_ROWS};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for K=%llu rows=%llu half=%d", (int)r, (unsigned long long)K,
               (unsigned long long)rows, (int)half);
@@ -523,10 +533,14 @@ static int set_smem(Kern k) {
 
 template <bool F16>
 static int set_smem_all() {
-  return set_smem(layer_tc_kernel<4, false, F16>) || set_smem(layer_tc_kernel<4, true, F16>) ||
-         set_smem(layer_tc_kernel<1, false, F16>) || set_smem(layer_tc_kernel<1, true, F16>) ||
-         set_smem(layer_tc_pair_kernel<4, false, F16>) || set_smem(layer_tc_pair_kernel<4, true, F16>) ||
-         set_smem(layer_tc_pair_kernel<1, false, F16>) || set_smem(layer_tc_pair_kernel<1, true, F16>);
+  return set_smem(layer_tc_kernel<4, false, F16, 64>) || set_smem(layer_tc_kernel<4, true, F16, 64>) ||
+         set_smem(layer_tc_kernel<1, false, F16, 64>) || set_smem(layer_tc_kernel<1, true, F16, 64>) ||
+         set_smem(layer_tc_pair_kernel<4, false, F16, 64>) || set_smem(layer_tc_pair_kernel<4, true, F16, 64>) ||
+         set_smem(layer_tc_pair_kernel<1, false, F16, 64>) || set_smem(layer_tc_pair_kernel<1, true, F16, 64>);
+}
+static int set_smem_wide() {
+  return set_smem(layer_tc_pair_kernel<4, false, true, 128>) || set_smem(layer_tc_pair_kernel<4, true, true, 128>) ||
+         set_smem(layer_tc_pair_kernel<1, false, true, 128>) || set_smem(layer_tc_pair_kernel<1, true, true, 128>);
 }
 
 int tc_init(fps_ctx* ctx) {
@@ -538,12 +552,16 @@ int tc_init(fps_ctx* ctx) {
   TcState* s = new TcState();
   ctx->tc_state = s;
   s->pair = getenv("FPS_TC_PAIR") ? atoi(getenv("FPS_TC_PAIR")) : 1;
+  s->rb = getenv("FPS_TC_ROWB") ? atoi(getenv("FPS_TC_ROWB")) : 128;
+  FPS_REQUIRE(s->rb == 64 || s->rb == 128, "FPS_TC_ROWB must be 64 or 128");
   for (int l = 0; l < NLAYER; ++l) {
     const Layer& L = ctx->layer[l];
     if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, FPW, false)) return 1;
     if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, FPW, false)) return 1;
     if (make_map(enc, &s->w_hi16[l], L.w_hi16, L.Kp, FPW, true)) return 1;
     if (make_map(enc, &s->w_lo16[l], L.w_lo16, L.Kp, FPW, true)) return 1;
+    if (make_map(enc, &s->w_hi16w[l], L.w_hi16, L.Kp, FPW, true, 128)) return 1;
+    if (make_map(enc, &s->w_lo16w[l], L.w_lo16, L.Kp, FPW, true, 128)) return 1;
   }
   const uint64_t cap_rows = (uint64_t)ctx->chunk * NSTREAM;
   for (int b = 0; b < 2; ++b) {
@@ -555,9 +573,11 @@ int tc_init(fps_ctx* ctx) {
       if (make_map(enc, &s->act_lo[b][kv], ctx->act[b].lo, Ks[kv], cap_rows, false)) return 1;
       if (make_map(enc, &s->act_hi16[b][kv], ctx->act[b].hi16, Ks[kv], cap_rows, true)) return 1;
       if (make_map(enc, &s->act_lo16[b][kv], ctx->act[b].lo16, Ks[kv], cap_rows, true)) return 1;
+      if (make_map(enc, &s->act_hi16w[b][kv], ctx->act[b].hi16, Ks[kv], cap_rows, true, 128)) return 1;
+      if (make_map(enc, &s->act_lo16w[b][kv], ctx->act[b].lo16, Ks[kv], cap_rows, true, 128)) return 1;
     }
   }
-  if (set_smem_all<false>() || set_smem_all<true>()) return 1;
+  if (set_smem_all<false>() || set_smem_all<true>() || set_smem_wide()) return 1;
   return 0;
 }
 
@@ -604,7 +624,9 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.DH = DH;
   P.ld = ld;
   P.rows = points * streams;
-  P.nk = L.Kp / (f16 ? 2 * TK : TK);
+  const bool wide = f16 && s->pair && s->rb == 128;     // 128-byte slab rows (SWIZZLE_128B)
+  const int slab_k = (wide ? 128 : 64) / (f16 ? 2 : 4);   // K elements per slab
+  P.nk = (L.Kp + slab_k - 1) / slab_k;                    // an overhanging last slab is zero-filled by TMA
   for (int i = 0; i < 4; ++i) {
     P.in_inv[i] = f16 ? 1.0f / (W16_SCALE * ctx->act_scale[l].s[i]) : 1.0f;
     P.out_sc[i] = ctx->act_scale[l + 1 < NLAYER ? l + 1 : l].s[i];
@@ -613,7 +635,6 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   static const int stats = getenv("FPS_TC_STATS") ? atoi(getenv("FPS_TC_STATS")) : 0;
   P.stats = stats;
   static const int seg_env = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : 0;
-  const int slab_k = f16 ? 2 * TK : TK;
   // K per tensor-core accumulation segment: 192 (FP16x2: 3 segments + a 128 tail per 704) or 128 (3xTF32)
   const int seg = seg_env ? seg_env : (f16 ? 192 : 128) / slab_k;
   P.seg = seg;
@@ -622,26 +643,35 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.gain = 1.0f + (kenv ? (float)atof(kenv) : kappa_of(seg * slab_k, f16));
   P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail * slab_k, f16));
   const int ncta = s->pair ? 2 : 1;
+  {
+    const int stage_bytes = (wide ? 128 : 64) * BOX_ROWS * (2 + 2 * (TN / BOX_ROWS / ncta));
+    static const int stages_env = getenv("FPS_TC_STAGES") ? atoi(getenv("FPS_TC_STAGES")) : 0;
+    const int max_stages = RING_BYTES / stage_bytes;
+    P.stages = (stages_env > 0 && stages_env < max_stages) ? stages_env : max_stages;
+  }
   const int total = P.row_tiles * (N_FEAT_TILES / ncta);          // tiles of a CTA (pair)
   const int groups_max = ctx->sm_count / ncta;
   const int grid = (total < groups_max ? total : groups_max) * ncta;
-  const CUtensorMap& m1 = f16 ? s->w_hi16[l] : s->w_hi[l];
-  const CUtensorMap& m2 = f16 ? s->w_lo16[l] : s->w_lo[l];
-  const CUtensorMap& m3 = f16 ? s->act_hi16[b][kv] : s->act_hi[b][kv];
-  const CUtensorMap& m4 = f16 ? s->act_lo16[b][kv] : s->act_lo[b][kv];
-#define FPS_TC_LAUNCH(K_, S_, LAST_, F_) K_<S_, LAST_, F_><<<grid, TC_THREADS, TC_SMEM, st>>>(m1, m2, m3, m4, P)
-#define FPS_TC_PICK(K_, F_)                                                                  \
-  do {                                                                                       \
-    if (streams == 4) {                                                                      \
-      if (last) FPS_TC_LAUNCH(K_, 4, true, F_); else FPS_TC_LAUNCH(K_, 4, false, F_);        \
-    } else {                                                                                 \
-      if (last) FPS_TC_LAUNCH(K_, 1, true, F_); else FPS_TC_LAUNCH(K_, 1, false, F_);        \
-    }                                                                                        \
+  const CUtensorMap& m1 = wide ? s->w_hi16w[l] : f16 ? s->w_hi16[l] : s->w_hi[l];
+  const CUtensorMap& m2 = wide ? s->w_lo16w[l] : f16 ? s->w_lo16[l] : s->w_lo[l];
+  const CUtensorMap& m3 = wide ? s->act_hi16w[b][kv] : f16 ? s->act_hi16[b][kv] : s->act_hi[b][kv];
+  const CUtensorMap& m4 = wide ? s->act_lo16w[b][kv] : f16 ? s->act_lo16[b][kv] : s->act_lo[b][kv];
+#define FPS_TC_LAUNCH(K_, S_, LAST_, F_, RB_) \
+  K_<S_, LAST_, F_, RB_><<<grid, TC_THREADS, TC_SMEM, st>>>(m1, m2, m3, m4, P)
+#define FPS_TC_PICK(K_, F_, RB_)                                                                     \
+  do {                                                                                               \
+    if (streams == 4) {                                                                              \
+      if (last) FPS_TC_LAUNCH(K_, 4, true, F_, RB_); else FPS_TC_LAUNCH(K_, 4, false, F_, RB_);      \
+    } else {                                                                                         \
+      if (last) FPS_TC_LAUNCH(K_, 1, true, F_, RB_); else FPS_TC_LAUNCH(K_, 1, false, F_, RB_);      \
+    }                                                                                                \
   } while (0)
-  if (s->pair) {
-    if (f16) FPS_TC_PICK(layer_tc_pair_kernel, true); else FPS_TC_PICK(layer_tc_pair_kernel, false);
+  if (wide) {
+    FPS_TC_PICK(layer_tc_pair_kernel, true, 128);
+  } else if (s->pair) {
+    if (f16) FPS_TC_PICK(layer_tc_pair_kernel, true, 64); else FPS_TC_PICK(layer_tc_pair_kernel, false, 64);
   } else {
-    if (f16) FPS_TC_PICK(layer_tc_kernel, true); else FPS_TC_PICK(layer_tc_kernel, false);
+    if (f16) FPS_TC_PICK(layer_tc_kernel, true, 64); else FPS_TC_PICK(layer_tc_kernel, false, 64);
   }
 #undef FPS_TC_PICK
 #undef FPS_TC_LAUNCH
