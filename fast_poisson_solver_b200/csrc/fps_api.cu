@@ -194,6 +194,7 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   }
   ctx->partial_bytes = (size_t)1024 * 64 * 64 * sizeof(double);  // 32 MiB of split-K tiles
   FPS_CUDA(cudaMalloc(&ctx->partial, ctx->partial_bytes));
+  FPS_CUDA(cudaMalloc(&ctx->dh_cmax, FPW * sizeof(unsigned)));
   ctx->workspace_bytes = 4 * plane + ctx->partial_bytes;
   if (tc_init(ctx)) { fps_destroy(ctx); return 3; }
   *out = ctx;
@@ -204,6 +205,7 @@ int fps_destroy(fps_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   tc_destroy(ctx);
+  gram_i8_destroy(ctx);
   for (int l = 0; l < NLAYER; ++l) {
     cudaFree(ctx->layer[l].w_hi);
     cudaFree(ctx->layer[l].w_lo);
@@ -218,6 +220,7 @@ int fps_destroy(fps_ctx* ctx) {
     cudaFree(ctx->act[i].hi);
   }
   cudaFree(ctx->partial);
+  cudaFree(ctx->dh_cmax);
   delete ctx->prof;
   delete ctx;
   return 0;
@@ -291,6 +294,15 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
   const int streams = DH ? NSTREAM : 1;
   // value-only evaluation carries one stream, so four times as many points fit a workspace wave
   const int64_t wave = (int64_t)ctx->chunk * (NSTREAM / streams);
+  if (DH) {
+    // the tensor-core engine's last layer records max |DH| per feature for fps_gram_accum's int8 path
+    ctx->dh_cmax_of = nullptr;
+    if (ctx->engine == FPS_ENGINE_TCGEN05) {
+      FPS_CUDA(cudaMemsetAsync(ctx->dh_cmax, 0, FPW * sizeof(unsigned), st));
+      ctx->dh_cmax_of = DH;
+      ctx->dh_cmax_n = n;
+    }
+  }
   for (int64_t p0 = 0; p0 < n; p0 += wave) {
     const int64_t np = (n - p0 < wave) ? n - p0 : wave;
     int cur = 0;
@@ -315,10 +327,14 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
   return 0;
 }
 
-int fps_gram_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* G64, void* stream) {
+int fps_gram_accum(fps_ctx* ctx, float* A, int64_t n, int64_t ld, double* G64, void* stream) {
   FPS_REQUIRE(ctx && A && G64, "fps_gram_accum: null argument");
   FPS_REQUIRE(ld >= FP, "fps_gram_accum: ld=%lld < %d", (long long)ld, FP);
   ProfScope ps(ctx, FPS_PROF_GRAM, (cudaStream_t)stream);
+  // large n: exact int8 tensor-core Gram (gram_i8.cu); small n (boundary points, tests): fp64 DMMA
+  static const int i8 = getenv("FPS_GRAM_I8") ? atoi(getenv("FPS_GRAM_I8")) : 1;
+  static const int64_t i8_min = getenv("FPS_GRAM_I8_MIN") ? atoll(getenv("FPS_GRAM_I8_MIN")) : 16384;
+  if (i8 && n >= i8_min) return launch_gram_i8(ctx, A, ld, n, G64, FP, (cudaStream_t)stream);
   return launch_atb_f64(ctx, A, ld, FP, A, ld, FP, n, G64, FP, true, (cudaStream_t)stream);
 }
 

@@ -79,6 +79,10 @@ struct fps_ctx {
   size_t partial_bytes;
   size_t workspace_bytes;
   void* tc_state;         // engine-private (tensor maps), owned by layer_tc.cu
+  void* gi_state;         // int8 exact-Gram workspace, owned by gram_i8.cu (allocated on first use)
+  unsigned* dh_cmax;      // FPW words: per-feature max |DH| (float bits) of the last fps_features call (tcgen05 engine)
+  const float* dh_cmax_of;  // the DH buffer those maxima describe (null: none), and its row count
+  int64_t dh_cmax_n;
   double* w64[fps::NLAYER]; // fp64 engine: (FP, Kp) row-major weights, zero padded
   double* b64[fps::NLAYER]; // fp64 engine: (FP) biases
 };
@@ -121,6 +125,9 @@ void tc_destroy(fps_ctx* ctx);
 // symmetric: A == B, only tiles with j <= i are computed and mirrored.
 int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const float* B, int64_t ldb, int Ncols,
                    int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st);
+// Same Gram (symmetric A^T A, M = FP) on the int8 tensor cores with exact products (gram_i8.cu)
+int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, int64_t ldg, cudaStream_t st);
+void gram_i8_destroy(fps_ctx* ctx);
 int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st);
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
                            int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,

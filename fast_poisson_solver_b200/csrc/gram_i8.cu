@@ -1,0 +1,495 @@
+// Gram matrix G += A^T A (A = DH, n x 704 fp32; solver.py:167 `DH.t() @ DH`) on the INT8 tensor cores with
+// EXACT products and exact accumulation (an Ozaki-style error-free split), replacing the fp64-pipe DMMA path
+// for large n.  The normal matrix has cond ~1e15: the Gram must be positive semi-definite to
+// fp64 rounding or the Cholesky breaks down, and it must be the Gram of exactly the matrix that the RHS
+// projection uses (measured on the CPU oracle, G = 32: a Gram that is off by 1e-11 costs 1e-4 in u).  The fp64
+// pipe gives 35 TFLOP/s, the int8 tensor pipe 4.5 POP/s.
+//
+//   1. gi_colmax_kernel     per-column max |a|  ->  exponent e_f with |a[:, f]| < 2^e_f
+//   2. gi_split_kernel      X = rint(a * 2^(30 - e_f)), a 31-bit integer.  For |a| >= 2^(e_f - 7) this is a itself;
+//                           smaller elements move by < 2^-31 of the column maximum (< 1 % of one fp32 ulp of that
+//                           maximum) and are SNAPPED IN PLACE: A is overwritten by X 2^(e_f - 30), which is again
+//                           an fp32 number, so everything downstream (RHS projection, f_pred, the saved state)
+//                           sees exactly the matrix whose Gram is computed.  X is written as four balanced
+//                           radix-256 digits  X = d0 2^24 + d1 2^16 + d2 2^8 + d3,  d in [-128, 127], into int8
+//                           planes laid out K-major and blocked by 128-point slab for the tensor core:
+//                           planes[slab][digit][feature][128 points] - every TMA box is one contiguous 16 KiB
+//                           (a feature-major layout with 1 MiB between rows ran at half the speed)
+//   3. gram_i8_kernel       per (256 x 64) tile and K range:  Acc_o = sum_{a+b=o} D_a^T D_b  for ALL 16 digit pairs,
+//                           orders o = 0..6, with tcgen05.mma.kind::i8 into seven int32 TMEM accumulators
+//                           (exact; drained before 2^31 can be reached), cta_group::2 pairs, TMA-fed
+//   4. gi_reduce_kernel     G[r][c] += 2^(e_r + e_c - 12) * sum_splits sum_o 2^(-8 o) Acc_o   (fixed order, fp64)
+//
+// Every product and every partial sum is an exact integer; the only rounding is the final fp64 combination
+// (2^-53 relative), so G is the Gram of the stored A to fp64 rounding, bit-reproducible and independent of the
+// K split.  (Dropping the orders 5 and 6, 2^-37 of the product of the column maxima, was tried first: the
+// Cholesky then needs a diagonal shift and f_pred moves by 1.5e-4.)
+#include "fps_common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace fps {
+
+constexpr int GI_SL = 4;                    // int8 digits per value
+constexpr int GI_TM = 128;                  // feature rows per CTA (UMMA M = 256 per pair)
+constexpr int GI_TN = 64;                   // feature columns per tile (UMMA N); each CTA stages 32 of them
+constexpr int GI_NACC = 7;                  // digit orders 0..6, one int32 accumulator each (448 TMEM columns)
+constexpr int GI_SLAB = 128;                // points per digit-plane row chunk (split kernel granularity)
+constexpr int GI_ROWS = FPW;                // 768 feature rows per digit plane
+// K slab of the tensor-core kernel = RB points = one RB-byte swizzled row (template parameter):
+//   RB = 128: 88 KiB stages x 2;  RB = 64: 44 KiB stages x 5 (more loads in flight)
+constexpr int GI_RING = 220 * 1024;
+constexpr int GI_SMEM = GI_RING + 1024 + 256;
+constexpr int GI_THREADS = 320;             // TMA warp, MMA warp, 8 drain warps
+constexpr int GI_NTILES = 24;               // (256 x 64) tiles that touch the lower triangle of 768 x 768
+// points per TMEM drain: an order holds at most 4 digit pairs of magnitude <= 2^14 -> 2^16 per point;
+// 28 672 points keep every accumulator below 2^31
+constexpr int GI_SEG_POINTS = 28672;
+constexpr int GI_TILE_ELEMS = 2 * GI_TM * GI_TN;  // fp64 partial tile of a pair
+
+// row block I (256 features) needs the column blocks J (64 features) with 64 J <= 256 I + 255: 4 + 8 + 12
+__host__ __device__ inline void gi_tile(int t, int& I, int& J) {
+  if (t < 4) { I = 0; J = t; }
+  else if (t < 12) { I = 1; J = t - 4; }
+  else { I = 2; J = t - 12; }
+}
+
+// ---- 1. column maxima -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gi_colmax_kernel(const float* __restrict__ A, int64_t ld, int64_t n, int64_t rows_per_cta, unsigned* __restrict__ cmax) {
+  const int t = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+  const bool has2 = t + 512 < FP;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+  for (int64_t r = r0; r < r1; r += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r + u < r1) {
+        const float* row = A + (r + u) * ld;
+        m0 = fmaxf(m0, fabsf(__ldg(row + t)));
+        m1 = fmaxf(m1, fabsf(__ldg(row + t + 256)));
+        if (has2) m2 = fmaxf(m2, fabsf(__ldg(row + t + 512)));
+      }
+    }
+  }
+  atomicMax(cmax + t, __float_as_uint(m0));
+  atomicMax(cmax + t + 256, __float_as_uint(m1));
+  if (has2) atomicMax(cmax + t + 512, __float_as_uint(m2));
+}
+
+// exponent e with max < 2^e, and the fixed-point scale 2^(30 - e) with its inverse (fp32 powers of two; e is
+// clamped to >= -90 so that both stay normal numbers: a column below 2^-90 is kept on a coarser grid)
+__global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int* __restrict__ exps, float2* __restrict__ scale) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= GI_ROWS) return;
+  int e = 0;
+  if (f < FP) {
+    const unsigned bits = cmax[f];
+    const int E = (int)(bits >> 23);
+    e = bits ? ((E > 0 ? E : 1) - 126) : 0;
+    if (e < -90) e = -90;
+  }
+  exps[f] = e;
+  scale[f] = make_float2(ldexpf(1.0f, 30 - e), ldexpf(1.0f, e - 30));
+}
+
+// ---- 2. digit split + transpose -------------------------------------------------------------------
+// CTA = 128 points x 64 features.  Reads are coalesced along the feature axis, the digits go through shared
+// memory (row pitch 33 words: conflict-free both ways) and leave as 128-byte rows along the point axis.
+__global__ void __launch_bounds__(256)
+gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, const float2* __restrict__ scale,
+                int8_t* __restrict__ planes, int64_t n_ld) {
+  __shared__ uint32_t sm[GI_SL][64][33];
+  const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int fh = w & 1, pq = w >> 1;
+  const int fl = fh * 32 + lane;
+  const int f = blockIdx.y * 64 + fl;
+  const float sc = scale[f].x, inv_sc = scale[f].y;   // powers of two: both products below are exact
+  const int64_t pbase = (int64_t)blockIdx.x * GI_SLAB + pq * 32;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    uint32_t word[GI_SL] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t p = pbase + it * 4 + u;
+      const float v = (p < n) ? A[p * ld + f] : 0.f;
+      int X = __float2int_rn(v * sc);
+      const float snapped = (float)X * inv_sc;   // exact: X has at most 24 significant bits
+      if (snapped != v) A[p * ld + f] = snapped;
+#pragma unroll
+      for (int s = GI_SL - 1; s >= 1; --s) {
+        const int d = ((X + 128) & 255) - 128;   // balanced digit in [-128, 127]
+        X = (X - d) >> 8;                         // exact
+        word[s] |= (uint32_t)(d & 255) << (8 * u);
+      }
+      word[0] |= (uint32_t)(X & 255) << (8 * u);  // |X| <= 64 here
+    }
+#pragma unroll
+    for (int s = 0; s < GI_SL; ++s) sm[s][fl][pq * 8 + it] = word[s];
+  }
+  __syncthreads();
+  // planes[slab][digit][feature][128]: a (digit, 64-feature) group is 8 KiB of consecutive bytes
+  int8_t* slab = planes + (int64_t)blockIdx.x * (GI_SL * GI_ROWS * GI_SLAB);
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    const int row = w * 32 + rr;
+    const int s = row / 64, rfl = row % 64;
+    *reinterpret_cast<uint32_t*>(slab + ((int64_t)s * GI_ROWS + blockIdx.y * 64 + rfl) * GI_SLAB + lane * 4) = sm[s][rfl][lane];
+  }
+}
+
+// ---- 3. the tensor-core kernel --------------------------------------------------------------------
+// One instruction covers one A digit against ALL FOUR B digits: the B operand of a tile is the stack
+//   B' = [D_0; D_1; D_2; D_3]  (4 x 64 feature rows = UMMA N 256; CTA 0 of the pair stages digits 0, 1, CTA 1 digits 2, 3)
+// and the MMA with A = D_a writes the 256-column TMEM window that starts at column 64 a, so that column group o
+// (64 columns) accumulates every digit pair with a + b = o:
+//   window(a) = [64 a, 64 a + 256)  =  orders a, a + 1, a + 2, a + 3.
+// Four N = 256 instructions per 32 points instead of sixteen N = 64 ones: the narrow form re-read the 4 KiB A tile
+// from shared memory sixteen times and was bound by shared-memory bandwidth at 47 % tensor-pipe activity.
+// All MMAs accumulate; the drain warps zero the accumulators after reading them (tcgen05.st).
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t da, uint64_t db) {
+  // kind::i8: D s32 (c_format 2), A and B signed 8-bit (format 1), K-major, M = 256 (pair), N = 256, K = 32
+  constexpr uint32_t idesc =
+      (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((GI_SL * GI_TN) >> 3) << 17) | ((uint32_t)((2 * GI_TM) >> 4) << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+      : "memory");
+}
+
+// 32 lanes x 16 consecutive columns of raw 32-bit words
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// zero 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const int z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+
+struct GiParams {
+  double* partial;       // nitems x (256 x 64) fp64
+  int slabs_total;       // ceil(n / RB)
+  int slabs_per_split;
+  int nitems;            // GI_NTILES * nsplit; item = split * GI_NTILES + tile
+};
+
+template <int RB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_THREADS, 1)
+gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GiParams P) {
+  constexpr int GI_A_BYTES = GI_TM * RB;            // per digit: 128 feature rows of this CTA
+  constexpr int GI_B_BYTES = GI_TN * RB;            // per digit: all 64 feature rows of the column block
+  constexpr int GI_STAGE = GI_SL * GI_A_BYTES + (GI_SL / 2) * GI_B_BYTES;   // this CTA stages 2 of the 4 B digits
+  constexpr int GI_STAGES = GI_RING / GI_STAGE;
+  constexpr int GI_SEG_SLABS = GI_SEG_POINTS / RB;
+  static_assert(GI_STAGES >= 2 && GI_STAGES <= 8, "ring depth");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + GI_RING;
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_tfull = bar_base + 128, bar_tempty = bar_base + 136;
+  const uint32_t tmem_slot = bar_base + 144;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rank = (int)cluster_ctarank();
+  const int group = blockIdx.x / 2, ngroups = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < GI_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 16);  // one arrive per drain warp of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs; bytes are counted on the leader's barrier) =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = group; item < P.nitems; item += ngroups) {
+        int I, J;
+        gi_tile(item % GI_NTILES, I, J);
+        const int kb0 = (item / GI_NTILES) * P.slabs_per_split;
+        const int kb1 = min(P.slabs_total, kb0 + P.slabs_per_split);
+        const int arow = I * 2 * GI_TM + rank * GI_TM, brow = J * GI_TN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * GI_STAGE;
+          const uint32_t full = bar_full + 8 * stage;
+          if (rank == 0) mbar_expect_tx(full, 2 * GI_STAGE);
+          const int kcol = (kb * RB) % GI_SLAB, rbase = (kb * RB) / GI_SLAB * GI_SL;
+#pragma unroll
+          for (int s = 0; s < GI_SL; ++s)
+            tma_load_2d<2>(sa + s * GI_A_BYTES, &tmA, full, kcol, (rbase + s) * GI_ROWS + arow);
+#pragma unroll
+          for (int s = 0; s < GI_SL / 2; ++s)   // B' rows [128 rank, 128 rank + 128) = digits 2 rank, 2 rank + 1
+            tma_load_2d<2>(sa + GI_SL * GI_A_BYTES + s * GI_B_BYTES, &tmB, full, kcol,
+                           (rbase + 2 * rank + s) * GI_ROWS + brow);
+          if (++stage == GI_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (pair leader) =================
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int item = group; item < P.nitems; item += ngroups) {
+        const int kb0 = (item / GI_NTILES) * P.slabs_per_split;
+        const int kb1 = min(P.slabs_total, kb0 + P.slabs_per_split);
+        for (int ks = kb0; ks < kb1; ks += GI_SEG_SLABS) {
+          const int ke = min(kb1, ks + GI_SEG_SLABS);
+          mbar_wait(bar_tempty, tphase);  // the drain warps have read and zeroed the accumulators
+          tphase ^= 1;
+          tc_fence_after();
+          for (int kb = ks; kb < ke; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * GI_STAGE;
+            const uint64_t db = umma_desc<RB>(sa + GI_SL * GI_A_BYTES);
+#pragma unroll
+            for (int j = 0; j < RB / 32; ++j) {  // 32 bytes (= 32 points) of K per instruction
+              const uint64_t adv = (uint64_t)((j * 32) >> 4);
+#pragma unroll
+              for (int a = 0; a < GI_SL; ++a)
+                umma_i8_pair(tmem_base + a * GI_TN, umma_desc<RB>(sa + a * GI_A_BYTES) + adv, db + adv);
+            }
+            umma_commit<2>(bar_empty + 8 * stage);
+            if (++stage == GI_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit<2>(bar_tfull);
+        }
+      }
+    }
+  } else {
+    // ================= drain warps 2..9: int32 accumulators -> fp64 partial tile =================
+    const int quad = warp % 4;          // TMEM lanes [32 quad, 32 quad + 32)
+    const int half = (warp - 2) / 4;    // 32 of the 64 columns of every order
+    const uint32_t taddr = tmem_base + half * (GI_TN / 2) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+    for (int o = 0; o < GI_NACC; ++o)
+#pragma unroll
+      for (int c = 0; c < GI_TN / 32; ++c) tmem_zero16(taddr + o * GI_TN + c * 16);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(bar_tempty);
+    uint32_t tphase = 0;
+    for (int item = group; item < P.nitems; item += ngroups) {
+      const int kb0 = (item / GI_NTILES) * P.slabs_per_split;
+      const int kb1 = min(P.slabs_total, kb0 + P.slabs_per_split);
+      double* out = P.partial + (size_t)item * GI_TILE_ELEMS + (size_t)(rank * GI_TM + quad * 32 + lane) * GI_TN + half * (GI_TN / 2);
+      bool first_seg = true;
+      for (int ks = kb0; ks < kb1; ks += GI_SEG_SLABS) {
+        mbar_wait(bar_tfull, tphase);
+        tphase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < GI_TN / 32; ++c) {
+          int v[GI_NACC][16];
+#pragma unroll
+          for (int o = 0; o < GI_NACC; ++o) tmem_ld16(taddr + o * GI_TN + c * 16, v[o]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int o = 0; o < GI_NACC; ++o) tmem_zero16(taddr + o * GI_TN + c * 16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            double g = (double)v[GI_NACC - 1][i];
+#pragma unroll
+            for (int o = GI_NACC - 2; o >= 0; --o) g = fma(g, 0.00390625, (double)v[o][i]);  // sum_o 2^(-8 o) Acc_o
+            if (!first_seg) g += out[c * 16 + i];
+            out[c * 16 + i] = g;
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_tempty);
+        first_seg = false;
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- 4. fixed-order reduction of the K splits, scaling, symmetric write-back ------------------------
+__global__ void __launch_bounds__(256)
+gi_reduce_kernel(const double* __restrict__ partial, int nsplit, const int* __restrict__ exps, double* __restrict__ G,
+                 int64_t ldg) {
+  int I, J;
+  gi_tile(blockIdx.x, I, J);
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < GI_TILE_ELEMS; e += gridDim.y * blockDim.x) {
+    const int r = I * 2 * GI_TM + e / GI_TN, c = J * GI_TN + e % GI_TN;
+    if (r >= FP || c > r) continue;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * GI_NTILES + blockIdx.x) * GI_TILE_ELEMS + e];
+    s = ldexp(s, exps[r] + exps[c] - 12);
+    G[(int64_t)r * ldg + c] += s;
+    if (c < r) G[(int64_t)c * ldg + r] += s;
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------
+struct GiState {
+  int8_t* planes = nullptr;
+  int64_t cap_points = 0;   // points the planes can hold (multiple of 128)
+  double* partial = nullptr;
+  unsigned* cmax = nullptr;
+  int* exps = nullptr;
+  float2* scale = nullptr;
+  void* encode = nullptr;
+  bool smem_set = false;
+};
+
+typedef CUresult (*GiEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int64_t GI_MAX_CHUNK = 1 << 20;   // points per pass: 3 GiB of digit planes
+constexpr int GI_MAX_SPLIT = 12;            // 24 tiles x 12 splits = 288 items = 3.9 waves of 74 pairs
+
+void gram_i8_destroy(fps_ctx* ctx) {
+  GiState* s = static_cast<GiState*>(ctx->gi_state);
+  if (!s) return;
+  cudaFree(s->planes);
+  cudaFree(s->partial);
+  cudaFree(s->cmax);
+  delete s;
+  ctx->gi_state = nullptr;
+}
+
+static int gi_prepare(fps_ctx* ctx, int64_t points) {
+  GiState* s = static_cast<GiState*>(ctx->gi_state);
+  if (!s) {
+    s = new GiState();
+    ctx->gi_state = s;
+    cudaDriverEntryPointQueryResult qres;
+    FPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &s->encode, cudaEnableDefault, &qres));
+    FPS_REQUIRE(s->encode && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    FPS_CUDA(cudaMalloc(&s->partial, (size_t)GI_NTILES * GI_MAX_SPLIT * GI_TILE_ELEMS * sizeof(double)));
+    // cmax (768 u32) | exps (768 i32) | scale (768 f64)
+    FPS_CUDA(cudaMalloc(&s->cmax, GI_ROWS * (sizeof(unsigned) + sizeof(int) + sizeof(double))));
+    s->exps = reinterpret_cast<int*>(s->cmax + GI_ROWS);
+    s->scale = reinterpret_cast<float2*>(s->exps + GI_ROWS);
+    FPS_CUDA(cudaFuncSetAttribute(gram_i8_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+    FPS_CUDA(cudaFuncSetAttribute(gram_i8_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+    ctx->workspace_bytes += (size_t)GI_NTILES * GI_MAX_SPLIT * GI_TILE_ELEMS * sizeof(double);
+  }
+  const int64_t need = (points + GI_SLAB - 1) / GI_SLAB * GI_SLAB;
+  if (need > s->cap_points) {
+    if (s->planes) {
+      FPS_CUDA(cudaFree(s->planes));
+      ctx->workspace_bytes -= (size_t)GI_SL * GI_ROWS * s->cap_points;
+      s->planes = nullptr;
+      s->cap_points = 0;
+    }
+    FPS_CUDA(cudaMalloc(&s->planes, (size_t)GI_SL * GI_ROWS * need));
+    s->cap_points = need;
+    ctx->workspace_bytes += (size_t)GI_SL * GI_ROWS * need;
+  }
+  return 0;
+}
+
+static int gi_make_map(GiState* s, CUtensorMap* m, const int8_t* base, int64_t n, int64_t n_ld, int box_rows, int rb) {
+  (void)n;
+  cuuint64_t dims[2] = {(cuuint64_t)GI_SLAB, (cuuint64_t)(n_ld / GI_SLAB) * (GI_SL * GI_ROWS)};
+  cuuint64_t strides[1] = {(cuuint64_t)GI_SLAB};
+  cuuint32_t box[2] = {(cuuint32_t)rb, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((GiEncodeFn)s->encode)(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FPS_REQUIRE(r == CUDA_SUCCESS, "gram_i8: cuTensorMapEncodeTiled failed (%d), n=%lld", (int)r, (long long)n);
+  return 0;
+}
+
+// G (FP x FP, ldg) += A^T A over n rows of A (n x >= FP, lda), lower triangle computed and mirrored.
+// A is snapped in place to the per-column fixed-point grid (see the header).
+int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, int64_t ldg, cudaStream_t st) {
+  if (n <= 0) return 0;
+  // FPS_GRAM_I8_CHUNK: points per pass (tests exercise the multi-pass loop with a small value)
+  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : GI_MAX_CHUNK;
+  FPS_REQUIRE(max_chunk >= GI_SLAB, "FPS_GRAM_I8_CHUNK must be at least %d", GI_SLAB);
+  const int64_t chunk = n < max_chunk ? n : max_chunk;
+  if (int rc = gi_prepare(ctx, chunk)) return rc;
+  GiState* s = static_cast<GiState*>(ctx->gi_state);
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
+    float* Ac = A + p0 * lda;
+    const int64_t n_ld = (np + GI_SLAB - 1) / GI_SLAB * GI_SLAB;
+    // column maxima: recorded by the feature kernel when A is the DH it has just produced (a bound over all
+    // n rows is valid for every chunk), else one streaming pass
+    const bool have_cmax = ctx->dh_cmax_of == A && ctx->dh_cmax_n == n;
+    if (!have_cmax) {
+      FPS_CUDA(cudaMemsetAsync(s->cmax, 0, GI_ROWS * sizeof(unsigned), st));
+      int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (np + 63) / 64);
+      const int64_t rpc = ((np + ctas - 1) / ctas + 3) / 4 * 4;
+      ctas = (np + rpc - 1) / rpc;
+      gi_colmax_kernel<<<(unsigned)ctas, 256, 0, st>>>(Ac, lda, np, rpc, s->cmax);
+      count_launch(1);
+    }
+    gi_exps_kernel<<<(GI_ROWS + 255) / 256, 256, 0, st>>>(have_cmax ? ctx->dh_cmax : s->cmax, s->exps, s->scale);
+    {
+      dim3 grid((unsigned)(n_ld / GI_SLAB), FP / 64);
+      gi_split_kernel<<<grid, 256, 0, st>>>(Ac, lda, np, s->scale, s->planes, n_ld);
+    }
+    FPS_CUDA(cudaGetLastError());
+    CUtensorMap tmA, tmB;
+    static const int rb = getenv("FPS_GRAM_ROWB") ? atoi(getenv("FPS_GRAM_ROWB")) : 128;
+    FPS_REQUIRE(rb == 64 || rb == 128, "FPS_GRAM_ROWB must be 64 or 128");
+    if (gi_make_map(s, &tmA, s->planes, np, n_ld, GI_TM, rb)) return 2;
+    if (gi_make_map(s, &tmB, s->planes, np, n_ld, GI_TN, rb)) return 2;
+    GiParams P;
+    P.partial = s->partial;
+    P.slabs_total = (int)(n_ld / rb);
+    const int pairs = ctx->sm_count / 2;
+    int nsplit = 1;
+    if (P.slabs_total >= GI_MAX_SPLIT * 4) nsplit = GI_MAX_SPLIT;
+    else if (P.slabs_total >= 3) nsplit = 3;   // 72 items: one wave
+    P.slabs_per_split = (P.slabs_total + nsplit - 1) / nsplit;
+    nsplit = (P.slabs_total + P.slabs_per_split - 1) / P.slabs_per_split;
+    P.nitems = GI_NTILES * nsplit;
+    const int groups = P.nitems < pairs ? P.nitems : pairs;
+    if (rb == 128) gram_i8_kernel<128><<<groups * 2, GI_THREADS, GI_SMEM, st>>>(tmA, tmB, P);
+    else gram_i8_kernel<64><<<groups * 2, GI_THREADS, GI_SMEM, st>>>(tmA, tmB, P);
+    FPS_CUDA(cudaGetLastError());
+    gi_reduce_kernel<<<dim3(GI_NTILES, 8), 256, 0, st>>>(s->partial, nsplit, s->exps, G, ldg);
+    FPS_CUDA(cudaGetLastError());
+    count_launch(4);
+  }
+  return 0;
+}
+
+}  // namespace fps

@@ -79,8 +79,13 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n,
 
 /* Replaces `DH.t() @ DH` (solver.py:167).  G64 (FPS_FP, FPS_FP) float64 += A^T A over the n rows
  * of A (n, ld) float32; both triangles are written.  Accumulating (beta = 1) so that callers can
- * chunk or shard rows; zero G64 first.                                                          */
-int fps_gram_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* G64, void* stream);
+ * chunk or shard rows; zero G64 first.
+ * For n >= 16384 the product runs on the int8 tensor cores with exact integer arithmetic
+ * (csrc/gram_i8.cu).  That path SNAPS A IN PLACE to a per-column 31-bit fixed-point grid: elements
+ * below 2^-7 of their column maximum move by less than 2^-31 of that maximum (under 1 % of one
+ * fp32 ulp of the maximum), all others are unchanged, and G64 receives the Gram of the stored A
+ * to fp64 rounding.  Call it before anything else consumes A (fps_project_rhs, fps_reconstruct). */
+int fps_gram_accum(fps_ctx* ctx, float* A, int64_t n, int64_t ld, double* G64, void* stream);
 
 /* Replaces `Ht_bc @ ones` (solver.py:176-178): s64 (FPS_FP) float64 += column sums of A.        */
 int fps_colsum_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double* s64, void* stream);

@@ -108,6 +108,67 @@ def test_gram_colsum_project_reconstruct_kernels(solver_factory):
             assert np.allclose(out.cpu().numpy(), ref.astype(np.float32), rtol=2e-7, atol=1e-5), (n, B)
 
 
+def test_gram_int8_exact_path(solver_factory):
+    """n >= 16384 rows: the Gram runs on the int8 tensor cores (csrc/gram_i8.cu).  It snaps A in place to a
+    per-column 31-bit grid and must return the Gram of the stored A to fp64 rounding, reproducibly."""
+    from fast_poisson_solver_b200 import _lib
+
+    s = solver_factory()
+    lib, ctx, st = s._lib, s._ctx, s._stream()
+    rng = np.random.default_rng(5)
+    for n in (16384, 40001):
+        a = rng.standard_normal((n, 704)) * np.exp(2.0 * rng.standard_normal((n, 704)))   # heavy tails
+        a *= 10.0 ** rng.uniform(-5, 5, size=(1, 704))                                     # column scales
+        a[:, 700:] = 0.0
+        a[:, 17] = 0.0                                                                     # an all-zero column
+        A = torch.tensor(a, dtype=torch.float32, device="cuda")
+        A0 = A.clone()
+        G = torch.zeros((704, 704), dtype=torch.float64, device="cuda")
+        _lib.check(lib.fps_gram_accum(ctx, A.data_ptr(), n, 704, G.data_ptr(), st), "gram")
+        torch.cuda.synchronize()
+        cmax = A0.abs().max(0).values
+        assert ((A - A0).abs() <= cmax[None, :] * 2.0 ** -30).all()       # |dA| <= half a grid step of 2^(e-30), e <= log2(cmax)+1
+        changed = (A != A0)
+        assert (A0.abs()[changed] < (cmax[None, :] * 2.0 ** -6).expand_as(A0)[changed]).all()   # only small elements move
+        A64 = A.double().cpu().numpy()
+        ref = A64.T @ A64
+        d = np.sqrt(np.maximum(np.diag(ref), 1e-300))
+        err = np.abs(G.cpu().numpy() - ref) / (d[:, None] * d[None, :])
+        assert err[:700, :700].max() < 1e-13, (n, err.max())
+        assert (G == G.T).all()
+        # second call: A is already on the grid -> unchanged, and the result is bit-identical
+        A1 = A.clone()
+        G2 = torch.zeros_like(G)
+        _lib.check(lib.fps_gram_accum(ctx, A.data_ptr(), n, 704, G2.data_ptr(), st), "gram")
+        torch.cuda.synchronize()
+        assert (A == A1).all() and (G2 == G).all()
+
+
+def test_gram_int8_multipass_in_subprocess():
+    """The chunk loop of the int8 Gram (n beyond one pass of digit planes), forced with FPS_GRAM_I8_CHUNK in a fresh process."""
+    import subprocess, sys, textwrap
+
+    code = textwrap.dedent("""
+        import os, sys, numpy as np, torch
+        sys.path.insert(0, %r)
+        os.chdir(%r)
+        from fast_poisson_solver_b200 import Solver, _lib
+        s = Solver(use_weights=False)
+        n = 40001
+        A = torch.randn(n, 704, device="cuda"); A[:, 700:] = 0
+        G = torch.zeros(704, 704, dtype=torch.float64, device="cuda")
+        _lib.check(s._lib.fps_gram_accum(s._ctx, A.data_ptr(), n, 704, G.data_ptr(), None), "gram")
+        torch.cuda.synchronize()
+        R = A.double().T @ A.double()
+        err = ((G - R).abs().max() / R.abs().max()).item()
+        assert err < 1e-14, err
+        print("MULTIPASS_OK", err)
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.getcwd())
+    env = dict(os.environ, FPS_GRAM_I8_CHUNK="8192")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "MULTIPASS_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_cholesky_and_batched_solve_kernels(solver_factory):
     import ctypes as C
     from fast_poisson_solver_b200 import _lib
