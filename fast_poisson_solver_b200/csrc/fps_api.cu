@@ -327,14 +327,21 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
   return 0;
 }
 
+// The exact int8 tensor-core path (gram_i8.cu) serves the Gram and the batched projection from the same row
+// count on, so that both always see the same (snapped) DH.  FPS_GRAM_I8=0 disables it, FPS_GRAM_I8_MIN moves
+// the threshold (tests).
+static bool use_i8(int64_t n) {
+  static const int i8 = getenv("FPS_GRAM_I8") ? atoi(getenv("FPS_GRAM_I8")) : 1;
+  static const int64_t i8_min = getenv("FPS_GRAM_I8_MIN") ? atoll(getenv("FPS_GRAM_I8_MIN")) : 16384;
+  return i8 && n >= i8_min;
+}
+
 int fps_gram_accum(fps_ctx* ctx, float* A, int64_t n, int64_t ld, double* G64, void* stream) {
   FPS_REQUIRE(ctx && A && G64, "fps_gram_accum: null argument");
   FPS_REQUIRE(ld >= FP, "fps_gram_accum: ld=%lld < %d", (long long)ld, FP);
   ProfScope ps(ctx, FPS_PROF_GRAM, (cudaStream_t)stream);
   // large n: exact int8 tensor-core Gram (gram_i8.cu); small n (boundary points, tests): fp64 DMMA
-  static const int i8 = getenv("FPS_GRAM_I8") ? atoi(getenv("FPS_GRAM_I8")) : 1;
-  static const int64_t i8_min = getenv("FPS_GRAM_I8_MIN") ? atoll(getenv("FPS_GRAM_I8_MIN")) : 16384;
-  if (i8 && n >= i8_min) return launch_gram_i8(ctx, A, ld, n, G64, FP, (cudaStream_t)stream);
+  if (use_i8(n)) return launch_gram_i8(ctx, A, ld, n, G64, FP, (cudaStream_t)stream);
   return launch_atb_f64(ctx, A, ld, FP, A, ld, FP, n, G64, FP, true, (cudaStream_t)stream);
 }
 
@@ -353,11 +360,13 @@ int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, co
                                 (cudaStream_t)stream);
 }
 
-int fps_project_rhs(fps_ctx* ctx, const float* DH, int64_t n, int64_t ld, const float* Fm, int64_t ldf, int B,
+int fps_project_rhs(fps_ctx* ctx, float* DH, int64_t n, int64_t ld, const float* Fm, int64_t ldf, int B,
                     double* R64, int64_t ldr, void* stream) {
   FPS_REQUIRE(ctx && DH && Fm && R64, "fps_project_rhs: null argument");
   FPS_REQUIRE(ld >= FP && ldf >= B && ldr >= B, "fps_project_rhs: bad leading dimension");
   ProfScope ps(ctx, FPS_PROF_PROJECT, (cudaStream_t)stream);
+  static const int i8_min_b = getenv("FPS_PROJECT_I8_MIN_B") ? atoi(getenv("FPS_PROJECT_I8_MIN_B")) : 32;
+  if (use_i8(n) && B >= i8_min_b) return launch_project_i8(ctx, DH, ld, Fm, ldf, B, n, R64, ldr, (cudaStream_t)stream);
   return launch_atb_f64(ctx, DH, ld, FP, Fm, ldf, B, n, R64, ldr, false, (cudaStream_t)stream);
 }
 

@@ -127,6 +127,8 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
                    int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st);
 // Same Gram (symmetric A^T A, M = FP) on the int8 tensor cores with exact products (gram_i8.cu)
 int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, int64_t ldg, cudaStream_t st);
+int launch_project_i8(fps_ctx* ctx, float* DH, int64_t lda, const float* F, int64_t ldf, int B, int64_t n, double* R,
+                      int64_t ldr, cudaStream_t st);
 void gram_i8_destroy(fps_ctx* ctx);
 int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st);
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,

@@ -20,6 +20,10 @@
 //                           (exact; drained before 2^31 can be reached), cta_group::2 pairs, TMA-fed
 //   4. gi_reduce_kernel     G[r][c] += 2^(e_r + e_c - 12) * sum_splits sum_o 2^(-8 o) Acc_o   (fixed order, fp64)
 //
+// The same engine computes the batched RHS projection R += DH^T F (solver.py:197 + :301, launch_project_i8):
+// A = the digit planes of DH (reused from the Gram when they are still valid), B = digit planes of F (a copy on
+// the grid of each right-hand side; F itself is not modified), rectangular tiling 3 x ceil(B / 64).
+//
 // Every product and every partial sum is an exact integer; the only rounding is the final fp64 combination
 // (2^-53 relative), so G is the Gram of the stored A to fp64 rounding, bit-reproducible and independent of the
 // K split.  (Dropping the orders 5 and 6, 2^-37 of the product of the column maxima, was tried first: the
@@ -58,34 +62,38 @@ __host__ __device__ inline void gi_tile(int t, int& I, int& J) {
 
 // ---- 1. column maxima -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gi_colmax_kernel(const float* __restrict__ A, int64_t ld, int64_t n, int64_t rows_per_cta, unsigned* __restrict__ cmax) {
-  const int t = threadIdx.x;
+gi_colmax_kernel(const float* __restrict__ A, int64_t ld, int64_t n, int ncols, int64_t rows_per_cta,
+                 unsigned* __restrict__ cmax) {
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
-  const bool has2 = t + 512 < FP;
-  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-  for (int64_t r = r0; r < r1; r += 4) {
+  for (int c0 = blockIdx.y * 768; c0 < min(ncols, (int)(blockIdx.y + 1) * 768); c0 += 768) {
+    const int t = c0 + threadIdx.x;
+    const bool h0 = t < ncols, h1 = t + 256 < ncols, h2 = t + 512 < ncols;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    for (int64_t r = r0; r < r1; r += 4) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (r + u < r1) {
-        const float* row = A + (r + u) * ld;
-        m0 = fmaxf(m0, fabsf(__ldg(row + t)));
-        m1 = fmaxf(m1, fabsf(__ldg(row + t + 256)));
-        if (has2) m2 = fmaxf(m2, fabsf(__ldg(row + t + 512)));
+      for (int u = 0; u < 4; ++u) {
+        if (r + u < r1) {
+          const float* row = A + (r + u) * ld;
+          if (h0) m0 = fmaxf(m0, fabsf(__ldg(row + t)));
+          if (h1) m1 = fmaxf(m1, fabsf(__ldg(row + t + 256)));
+          if (h2) m2 = fmaxf(m2, fabsf(__ldg(row + t + 512)));
+        }
       }
     }
+    if (h0) atomicMax(cmax + t, __float_as_uint(m0));
+    if (h1) atomicMax(cmax + t + 256, __float_as_uint(m1));
+    if (h2) atomicMax(cmax + t + 512, __float_as_uint(m2));
   }
-  atomicMax(cmax + t, __float_as_uint(m0));
-  atomicMax(cmax + t + 256, __float_as_uint(m1));
-  if (has2) atomicMax(cmax + t + 512, __float_as_uint(m2));
 }
 
 // exponent e with max < 2^e, and the fixed-point scale 2^(30 - e) with its inverse (fp32 powers of two; e is
 // clamped to >= -90 so that both stay normal numbers: a column below 2^-90 is kept on a coarser grid)
-__global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int* __restrict__ exps, float2* __restrict__ scale) {
+__global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int ncols, int rows, int* __restrict__ exps,
+                               float2* __restrict__ scale) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= GI_ROWS) return;
+  if (f >= rows) return;
   int e = 0;
-  if (f < FP) {
+  if (f < ncols) {
     const unsigned bits = cmax[f];
     const int E = (int)(bits >> 23);
     e = bits ? ((E > 0 ? E : 1) - 126) : 0;
@@ -98,14 +106,18 @@ __global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int* __restric
 // ---- 2. digit split + transpose -------------------------------------------------------------------
 // CTA = 128 points x 64 features.  Reads are coalesced along the feature axis, the digits go through shared
 // memory (row pitch 33 words: conflict-free both ways) and leave as 128-byte rows along the point axis.
+// SNAP: write X 2^(e - 30) back into A (the Gram / projection operand DH); otherwise A is read only (F).
+// rows = feature rows per digit plane (a multiple of 64 >= ncols); columns >= ncols produce zero digits.
+template <bool SNAP>
 __global__ void __launch_bounds__(256)
-gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, const float2* __restrict__ scale,
-                int8_t* __restrict__ planes, int64_t n_ld) {
+gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int rows, const float2* __restrict__ scale,
+                int8_t* __restrict__ planes) {
   __shared__ uint32_t sm[GI_SL][64][33];
   const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int fh = w & 1, pq = w >> 1;
   const int fl = fh * 32 + lane;
   const int f = blockIdx.y * 64 + fl;
+  const bool col_ok = f < ncols;
   const float sc = scale[f].x, inv_sc = scale[f].y;   // powers of two: both products below are exact
   const int64_t pbase = (int64_t)blockIdx.x * GI_SLAB + pq * 32;
 #pragma unroll
@@ -114,10 +126,12 @@ gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, const float2* __re
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t p = pbase + it * 4 + u;
-      const float v = (p < n) ? A[p * ld + f] : 0.f;
+      const float v = (col_ok && p < n) ? A[p * ld + f] : 0.f;
       int X = __float2int_rn(v * sc);
-      const float snapped = (float)X * inv_sc;   // exact: X has at most 24 significant bits
-      if (snapped != v) A[p * ld + f] = snapped;
+      if (SNAP) {
+        const float snapped = (float)X * inv_sc;   // exact: X has at most 24 significant bits
+        if (snapped != v) A[p * ld + f] = snapped;
+      }
 #pragma unroll
       for (int s = GI_SL - 1; s >= 1; --s) {
         const int d = ((X + 128) & 255) - 128;   // balanced digit in [-128, 127]
@@ -131,12 +145,12 @@ gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, const float2* __re
   }
   __syncthreads();
   // planes[slab][digit][feature][128]: a (digit, 64-feature) group is 8 KiB of consecutive bytes
-  int8_t* slab = planes + (int64_t)blockIdx.x * (GI_SL * GI_ROWS * GI_SLAB);
+  int8_t* slab = planes + (int64_t)blockIdx.x * ((int64_t)GI_SL * rows * GI_SLAB);
 #pragma unroll 4
   for (int rr = 0; rr < 32; ++rr) {
     const int row = w * 32 + rr;
     const int s = row / 64, rfl = row % 64;
-    *reinterpret_cast<uint32_t*>(slab + ((int64_t)s * GI_ROWS + blockIdx.y * 64 + rfl) * GI_SLAB + lane * 4) = sm[s][rfl][lane];
+    *reinterpret_cast<uint32_t*>(slab + ((int64_t)s * rows + blockIdx.y * 64 + rfl) * GI_SLAB + lane * 4) = sm[s][rfl][lane];
   }
 }
 
@@ -184,8 +198,19 @@ struct GiParams {
   double* partial;       // nitems x (256 x 64) fp64
   int slabs_total;       // ceil(n / RB)
   int slabs_per_split;
-  int nitems;            // GI_NTILES * nsplit; item = split * GI_NTILES + tile
+  int ntiles;            // symmetric: GI_NTILES (lower triangle); else 3 x tiles_j
+  int nitems;            // ntiles * nsplit; item = split * ntiles + tile
+  int sym;               // 1: Gram (B planes = A planes), 0: rectangular A^T B
+  int tiles_j;           // column blocks of 64 (rectangular case)
+  int rows_a, rows_b;    // feature rows per digit plane of the A / B operand
+  int slab_a0;           // first 128-point slab of this pass inside the A planes (B planes start at 0)
 };
+
+__device__ __forceinline__ void gi_item_tile(const GiParams& P, int item, int& I, int& J) {
+  const int t = item % P.ntiles;
+  if (P.sym) gi_tile(t, I, J);
+  else { I = t / P.tiles_j; J = t % P.tiles_j; }
+}
 
 template <int RB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GI_THREADS, 1)
@@ -233,8 +258,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t stage = 0, phase = 0;
       for (int item = group; item < P.nitems; item += ngroups) {
         int I, J;
-        gi_tile(item % GI_NTILES, I, J);
-        const int kb0 = (item / GI_NTILES) * P.slabs_per_split;
+        gi_item_tile(P, item, I, J);
+        const int kb0 = (item / P.ntiles) * P.slabs_per_split;
         const int kb1 = min(P.slabs_total, kb0 + P.slabs_per_split);
         const int arow = I * 2 * GI_TM + rank * GI_TM, brow = J * GI_TN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -242,14 +267,14 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_base + stage * GI_STAGE;
           const uint32_t full = bar_full + 8 * stage;
           if (rank == 0) mbar_expect_tx(full, 2 * GI_STAGE);
-          const int kcol = (kb * RB) % GI_SLAB, rbase = (kb * RB) / GI_SLAB * GI_SL;
+          const int kcol = (kb * RB) % GI_SLAB, slab = (kb * RB) / GI_SLAB;
 #pragma unroll
           for (int s = 0; s < GI_SL; ++s)
-            tma_load_2d<2>(sa + s * GI_A_BYTES, &tmA, full, kcol, (rbase + s) * GI_ROWS + arow);
+            tma_load_2d<2>(sa + s * GI_A_BYTES, &tmA, full, kcol, ((P.slab_a0 + slab) * GI_SL + s) * P.rows_a + arow);
 #pragma unroll
           for (int s = 0; s < GI_SL / 2; ++s)   // B' rows [128 rank, 128 rank + 128) = digits 2 rank, 2 rank + 1
             tma_load_2d<2>(sa + GI_SL * GI_A_BYTES + s * GI_B_BYTES, &tmB, full, kcol,
-                           (rbase + 2 * rank + s) * GI_ROWS + brow);
+                           ((P.sym ? P.slab_a0 + slab : slab) * GI_SL + 2 * rank + s) * P.rows_b + brow);
           if (++stage == GI_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -259,7 +284,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, tphase = 0;
       for (int item = group; item < P.nitems; item += ngroups) {
-        const int kb0 = (item / GI_NTILES) * P.slabs_per_split;
+        const int kb0 = (item / P.ntiles) * P.slabs_per_split;
         const int kb1 = min(P.slabs_total, kb0 + P.slabs_per_split);
         for (int ks = kb0; ks < kb1; ks += GI_SEG_SLABS) {
           const int ke = min(kb1, ks + GI_SEG_SLABS);
@@ -300,7 +325,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) mbar_arrive_leader(bar_tempty);
     uint32_t tphase = 0;
     for (int item = group; item < P.nitems; item += ngroups) {
-      const int kb0 = (item / GI_NTILES) * P.slabs_per_split;
+      const int kb0 = (item / P.ntiles) * P.slabs_per_split;
       const int kb1 = min(P.slabs_total, kb0 + P.slabs_per_split);
       double* out = P.partial + (size_t)item * GI_TILE_ELEMS + (size_t)(rank * GI_TM + quad * 32 + lane) * GI_TN + half * (GI_TN / 2);
       bool first_seg = true;
@@ -343,53 +368,63 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// ---- 4. fixed-order reduction of the K splits, scaling, symmetric write-back ------------------------
+// ---- 4. fixed-order reduction of the K splits, scaling, write-back ----------------------------------
+// C[r][c] += 2^(ea[r] + eb[c] - 12) * sum_splits partial;  symmetric: lower triangle computed, mirrored.
 __global__ void __launch_bounds__(256)
-gi_reduce_kernel(const double* __restrict__ partial, int nsplit, const int* __restrict__ exps, double* __restrict__ G,
-                 int64_t ldg) {
+gi_reduce_kernel(const double* __restrict__ partial, int nsplit, int ntiles, int sym, int tiles_j, int M, int Nc,
+                 const int* __restrict__ ea, const int* __restrict__ eb, double* __restrict__ C, int64_t ldc) {
   int I, J;
-  gi_tile(blockIdx.x, I, J);
+  if (sym) gi_tile(blockIdx.x, I, J);
+  else { I = blockIdx.x / tiles_j; J = blockIdx.x % tiles_j; }
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < GI_TILE_ELEMS; e += gridDim.y * blockDim.x) {
     const int r = I * 2 * GI_TM + e / GI_TN, c = J * GI_TN + e % GI_TN;
-    if (r >= FP || c > r) continue;
+    if (r >= M || c >= Nc || (sym && c > r)) continue;
     double s = 0.0;
-    for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * GI_NTILES + blockIdx.x) * GI_TILE_ELEMS + e];
-    s = ldexp(s, exps[r] + exps[c] - 12);
-    G[(int64_t)r * ldg + c] += s;
-    if (c < r) G[(int64_t)c * ldg + r] += s;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[((size_t)sp * ntiles + blockIdx.x) * GI_TILE_ELEMS + e];
+    s = ldexp(s, ea[r] + eb[c] - 12);
+    C[(int64_t)r * ldc + c] += s;
+    if (sym && c < r) C[(int64_t)c * ldc + r] += s;
   }
 }
 
 // ---- host -----------------------------------------------------------------------------------------
-struct GiState {
-  int8_t* planes = nullptr;
-  int64_t cap_points = 0;   // points the planes can hold (multiple of 128)
-  double* partial = nullptr;
-  unsigned* cmax = nullptr;
+struct GiPlanes {            // digit planes of one operand: planes[slab][digit][rows][128]
+  int8_t* data = nullptr;
+  size_t cap_bytes = 0;
+  unsigned* cmax = nullptr;  // rows_cap x {u32 cmax, i32 exps, float2 scale}
   int* exps = nullptr;
   float2* scale = nullptr;
+  int rows_cap = 0;
+  int rows = 0;              // feature rows per digit plane of the current contents
+};
+
+struct GiState {
+  GiPlanes a, b;
+  double* partial = nullptr;
+  size_t partial_bytes = 0;
   void* encode = nullptr;
-  bool smem_set = false;
 };
 
 typedef CUresult (*GiEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-constexpr int64_t GI_MAX_CHUNK = 1 << 20;   // points per pass: 3 GiB of digit planes
-constexpr int GI_MAX_SPLIT = 12;            // 24 tiles x 12 splits = 288 items = 3.9 waves of 74 pairs
+constexpr int64_t GI_MAX_CHUNK = 1 << 20;          // points per Gram pass: 3 GiB of digit planes
+constexpr size_t GI_B_PLANE_BYTES = (size_t)5 << 30;  // budget for the digit planes of F per projection pass
 
 void gram_i8_destroy(fps_ctx* ctx) {
   GiState* s = static_cast<GiState*>(ctx->gi_state);
   if (!s) return;
-  cudaFree(s->planes);
+  cudaFree(s->a.data);
+  cudaFree(s->a.cmax);
+  cudaFree(s->b.data);
+  cudaFree(s->b.cmax);
   cudaFree(s->partial);
-  cudaFree(s->cmax);
   delete s;
   ctx->gi_state = nullptr;
 }
 
-static int gi_prepare(fps_ctx* ctx, int64_t points) {
+static int gi_state_get(fps_ctx* ctx, GiState** out) {
   GiState* s = static_cast<GiState*>(ctx->gi_state);
   if (!s) {
     s = new GiState();
@@ -397,33 +432,66 @@ static int gi_prepare(fps_ctx* ctx, int64_t points) {
     cudaDriverEntryPointQueryResult qres;
     FPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &s->encode, cudaEnableDefault, &qres));
     FPS_REQUIRE(s->encode && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-    FPS_CUDA(cudaMalloc(&s->partial, (size_t)GI_NTILES * GI_MAX_SPLIT * GI_TILE_ELEMS * sizeof(double)));
-    // cmax (768 u32) | exps (768 i32) | scale (768 f64)
-    FPS_CUDA(cudaMalloc(&s->cmax, GI_ROWS * (sizeof(unsigned) + sizeof(int) + sizeof(double))));
-    s->exps = reinterpret_cast<int*>(s->cmax + GI_ROWS);
-    s->scale = reinterpret_cast<float2*>(s->exps + GI_ROWS);
     FPS_CUDA(cudaFuncSetAttribute(gram_i8_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
     FPS_CUDA(cudaFuncSetAttribute(gram_i8_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
-    ctx->workspace_bytes += (size_t)GI_NTILES * GI_MAX_SPLIT * GI_TILE_ELEMS * sizeof(double);
   }
-  const int64_t need = (points + GI_SLAB - 1) / GI_SLAB * GI_SLAB;
-  if (need > s->cap_points) {
-    if (s->planes) {
-      FPS_CUDA(cudaFree(s->planes));
-      ctx->workspace_bytes -= (size_t)GI_SL * GI_ROWS * s->cap_points;
-      s->planes = nullptr;
-      s->cap_points = 0;
-    }
-    FPS_CUDA(cudaMalloc(&s->planes, (size_t)GI_SL * GI_ROWS * need));
-    s->cap_points = need;
-    ctx->workspace_bytes += (size_t)GI_SL * GI_ROWS * need;
+  *out = s;
+  return 0;
+}
+
+// grow-only buffers; workspace_bytes follows
+static int gi_reserve_planes(fps_ctx* ctx, GiPlanes& pl, int rows, int64_t points) {
+  const size_t need = (size_t)GI_SL * rows * ((points + GI_SLAB - 1) / GI_SLAB * GI_SLAB);
+  if (need > pl.cap_bytes) {
+    if (pl.data) { FPS_CUDA(cudaFree(pl.data)); ctx->workspace_bytes -= pl.cap_bytes; pl.data = nullptr; pl.cap_bytes = 0; }
+    FPS_CUDA(cudaMalloc(&pl.data, need));
+    pl.cap_bytes = need;
+    ctx->workspace_bytes += need;
+  }
+  if (rows > pl.rows_cap) {
+    if (pl.cmax) FPS_CUDA(cudaFree(pl.cmax));
+    FPS_CUDA(cudaMalloc(&pl.cmax, (size_t)rows * (sizeof(unsigned) + sizeof(int) + sizeof(float2))));
+    pl.scale = reinterpret_cast<float2*>(pl.cmax + 2 * (size_t)rows);   // 8-byte aligned: rows is a multiple of 64
+    pl.exps = reinterpret_cast<int*>(pl.cmax + rows);
+    pl.rows_cap = rows;
   }
   return 0;
 }
 
-static int gi_make_map(GiState* s, CUtensorMap* m, const int8_t* base, int64_t n, int64_t n_ld, int box_rows, int rb) {
-  (void)n;
-  cuuint64_t dims[2] = {(cuuint64_t)GI_SLAB, (cuuint64_t)(n_ld / GI_SLAB) * (GI_SL * GI_ROWS)};
+static int gi_reserve_partial(fps_ctx* ctx, GiState* s, int nitems) {
+  const size_t need = (size_t)nitems * GI_TILE_ELEMS * sizeof(double);
+  if (need > s->partial_bytes) {
+    if (s->partial) { FPS_CUDA(cudaFree(s->partial)); ctx->workspace_bytes -= s->partial_bytes; }
+    FPS_CUDA(cudaMalloc(&s->partial, need));
+    s->partial_bytes = need;
+    ctx->workspace_bytes += need;
+  }
+  return 0;
+}
+
+// column maxima (unless `known` supplies them) -> exponents -> digit planes of `np` rows of A starting at slab 0
+template <bool SNAP>
+static int gi_split(fps_ctx* ctx, GiPlanes& pl, float* A, int64_t lda, int64_t np, int ncols, int rows,
+                    const unsigned* known, cudaStream_t st) {
+  if (!known) {
+    FPS_CUDA(cudaMemsetAsync(pl.cmax, 0, (size_t)rows * sizeof(unsigned), st));
+    int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (np + 63) / 64);
+    const int64_t rpc = ((np + ctas - 1) / ctas + 3) / 4 * 4;
+    ctas = (np + rpc - 1) / rpc;
+    gi_colmax_kernel<<<dim3((unsigned)ctas, (unsigned)((ncols + 767) / 768)), 256, 0, st>>>(A, lda, np, ncols, rpc, pl.cmax);
+    count_launch(1);
+  }
+  gi_exps_kernel<<<(rows + 255) / 256, 256, 0, st>>>(known ? known : pl.cmax, ncols, rows, pl.exps, pl.scale);
+  const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
+  gi_split_kernel<SNAP><<<dim3((unsigned)slabs, (unsigned)(rows / 64)), 256, 0, st>>>(A, lda, np, ncols, rows, pl.scale,
+                                                                                       pl.data);
+  count_launch(2);
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int gi_make_map(GiState* s, CUtensorMap* m, const int8_t* base, int64_t slabs, int rows, int box_rows, int rb) {
+  cuuint64_t dims[2] = {(cuuint64_t)GI_SLAB, (cuuint64_t)slabs * GI_SL * rows};
   cuuint64_t strides[1] = {(cuuint64_t)GI_SLAB};
   cuuint32_t box[2] = {(cuuint32_t)rb, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
@@ -431,7 +499,58 @@ static int gi_make_map(GiState* s, CUtensorMap* m, const int8_t* base, int64_t n
                                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                                         rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FPS_REQUIRE(r == CUDA_SUCCESS, "gram_i8: cuTensorMapEncodeTiled failed (%d), n=%lld", (int)r, (long long)n);
+  FPS_REQUIRE(r == CUDA_SUCCESS, "gram_i8: cuTensorMapEncodeTiled failed (%d), slabs=%lld rows=%d", (int)r,
+              (long long)slabs, rows);
+  return 0;
+}
+
+// K split: items = ntiles x nsplit should fill whole waves of CTA pairs
+static int gi_pick_split(int ntiles, int slabs, int pairs) {
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ns = 1; ns <= 64 && ns <= slabs; ++ns) {
+    if (ns > 1 && slabs / ns < 8) break;            // keep the TMEM drain amortised
+    const int items = ntiles * ns;
+    const int waves = (items + pairs - 1) / pairs;
+    const double eff = (double)items / ((double)waves * pairs);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = ns; }
+    if (waves >= 8) break;
+  }
+  return best;
+}
+
+// one pass: C (M x Nc, ldc) += A^T B over the `slabs` 128-point slabs that start at slab_a0 of the A planes and at 0
+// of the B planes
+static int gi_run(fps_ctx* ctx, GiState* s, const GiPlanes& pa, int64_t slabs_in_a, int slab_a0, const GiPlanes& pb,
+                  int64_t slabs_in_b, int64_t slabs, bool sym, int M, int Nc, double* C, int64_t ldc, cudaStream_t st) {
+  static const int rb = getenv("FPS_GRAM_ROWB") ? atoi(getenv("FPS_GRAM_ROWB")) : 128;
+  FPS_REQUIRE(rb == 64 || rb == 128, "FPS_GRAM_ROWB must be 64 or 128");
+  CUtensorMap tmA, tmB;
+  if (gi_make_map(s, &tmA, pa.data, slabs_in_a, pa.rows, GI_TM, rb)) return 2;
+  if (gi_make_map(s, &tmB, pb.data, slabs_in_b, pb.rows, GI_TN, rb)) return 2;
+  GiParams P;
+  P.sym = sym ? 1 : 0;
+  P.tiles_j = (Nc + GI_TN - 1) / GI_TN;
+  P.ntiles = sym ? GI_NTILES : 3 * P.tiles_j;
+  P.rows_a = pa.rows;
+  P.rows_b = pb.rows;
+  P.slab_a0 = slab_a0;
+  P.slabs_total = (int)(slabs * (GI_SLAB / rb));
+  const int pairs = ctx->sm_count / 2;
+  int nsplit = gi_pick_split(P.ntiles, P.slabs_total, pairs);
+  P.slabs_per_split = (P.slabs_total + nsplit - 1) / nsplit;
+  nsplit = (P.slabs_total + P.slabs_per_split - 1) / P.slabs_per_split;
+  P.nitems = P.ntiles * nsplit;
+  if (int rc = gi_reserve_partial(ctx, s, P.nitems)) return rc;
+  P.partial = s->partial;
+  const int groups = P.nitems < pairs ? P.nitems : pairs;
+  if (rb == 128) gram_i8_kernel<128><<<groups * 2, GI_THREADS, GI_SMEM, st>>>(tmA, tmB, P);
+  else gram_i8_kernel<64><<<groups * 2, GI_THREADS, GI_SMEM, st>>>(tmA, tmB, P);
+  FPS_CUDA(cudaGetLastError());
+  gi_reduce_kernel<<<dim3(P.ntiles, 8), 256, 0, st>>>(s->partial, nsplit, P.ntiles, P.sym, P.tiles_j, M, Nc, pa.exps,
+                                                      pb.exps, C, ldc);
+  FPS_CUDA(cudaGetLastError());
+  count_launch(2);
   return 0;
 }
 
@@ -441,53 +560,54 @@ int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, in
   if (n <= 0) return 0;
   // FPS_GRAM_I8_CHUNK: points per pass (tests exercise the multi-pass loop with a small value)
   static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : GI_MAX_CHUNK;
-  FPS_REQUIRE(max_chunk >= GI_SLAB, "FPS_GRAM_I8_CHUNK must be at least %d", GI_SLAB);
+  FPS_REQUIRE(max_chunk >= GI_SLAB && (max_chunk & (max_chunk - 1)) == 0, "FPS_GRAM_I8_CHUNK must be a power of two >= 128");
   const int64_t chunk = n < max_chunk ? n : max_chunk;
-  if (int rc = gi_prepare(ctx, chunk)) return rc;
-  GiState* s = static_cast<GiState*>(ctx->gi_state);
+  GiState* s;
+  if (int rc = gi_state_get(ctx, &s)) return rc;
+  if (int rc = gi_reserve_planes(ctx, s->a, GI_ROWS, chunk)) return rc;
+  // column maxima: recorded by the feature kernel when A is the DH it has just produced (a bound over all n rows
+  // is valid for every chunk), else one streaming pass per chunk
+  const bool have_cmax = ctx->dh_cmax_of == A && ctx->dh_cmax_n == n;
   for (int64_t p0 = 0; p0 < n; p0 += chunk) {
     const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
-    float* Ac = A + p0 * lda;
-    const int64_t n_ld = (np + GI_SLAB - 1) / GI_SLAB * GI_SLAB;
-    // column maxima: recorded by the feature kernel when A is the DH it has just produced (a bound over all
-    // n rows is valid for every chunk), else one streaming pass
-    const bool have_cmax = ctx->dh_cmax_of == A && ctx->dh_cmax_n == n;
-    if (!have_cmax) {
-      FPS_CUDA(cudaMemsetAsync(s->cmax, 0, GI_ROWS * sizeof(unsigned), st));
-      int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (np + 63) / 64);
-      const int64_t rpc = ((np + ctas - 1) / ctas + 3) / 4 * 4;
-      ctas = (np + rpc - 1) / rpc;
-      gi_colmax_kernel<<<(unsigned)ctas, 256, 0, st>>>(Ac, lda, np, rpc, s->cmax);
-      count_launch(1);
-    }
-    gi_exps_kernel<<<(GI_ROWS + 255) / 256, 256, 0, st>>>(have_cmax ? ctx->dh_cmax : s->cmax, s->exps, s->scale);
-    {
-      dim3 grid((unsigned)(n_ld / GI_SLAB), FP / 64);
-      gi_split_kernel<<<grid, 256, 0, st>>>(Ac, lda, np, s->scale, s->planes, n_ld);
-    }
-    FPS_CUDA(cudaGetLastError());
-    CUtensorMap tmA, tmB;
-    static const int rb = getenv("FPS_GRAM_ROWB") ? atoi(getenv("FPS_GRAM_ROWB")) : 128;
-    FPS_REQUIRE(rb == 64 || rb == 128, "FPS_GRAM_ROWB must be 64 or 128");
-    if (gi_make_map(s, &tmA, s->planes, np, n_ld, GI_TM, rb)) return 2;
-    if (gi_make_map(s, &tmB, s->planes, np, n_ld, GI_TN, rb)) return 2;
-    GiParams P;
-    P.partial = s->partial;
-    P.slabs_total = (int)(n_ld / rb);
-    const int pairs = ctx->sm_count / 2;
-    int nsplit = 1;
-    if (P.slabs_total >= GI_MAX_SPLIT * 4) nsplit = GI_MAX_SPLIT;
-    else if (P.slabs_total >= 3) nsplit = 3;   // 72 items: one wave
-    P.slabs_per_split = (P.slabs_total + nsplit - 1) / nsplit;
-    nsplit = (P.slabs_total + P.slabs_per_split - 1) / P.slabs_per_split;
-    P.nitems = GI_NTILES * nsplit;
-    const int groups = P.nitems < pairs ? P.nitems : pairs;
-    if (rb == 128) gram_i8_kernel<128><<<groups * 2, GI_THREADS, GI_SMEM, st>>>(tmA, tmB, P);
-    else gram_i8_kernel<64><<<groups * 2, GI_THREADS, GI_SMEM, st>>>(tmA, tmB, P);
-    FPS_CUDA(cudaGetLastError());
-    gi_reduce_kernel<<<dim3(GI_NTILES, 8), 256, 0, st>>>(s->partial, nsplit, s->exps, G, ldg);
-    FPS_CUDA(cudaGetLastError());
-    count_launch(4);
+    s->a.rows = GI_ROWS;
+    if (int rc = gi_split<true>(ctx, s->a, A + p0 * lda, lda, np, FP, GI_ROWS, have_cmax ? ctx->dh_cmax : nullptr, st))
+      return rc;
+    const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
+    if (int rc = gi_run(ctx, s, s->a, slabs, 0, s->a, slabs, slabs, true, FP, FP, G, ldg, st)) return rc;
+  }
+  return 0;
+}
+
+// R (FP x B, ldr) += DH^T F over n rows; DH (n x >= FP, lda) is snapped in place like in launch_gram_i8 (a no-op
+// when the Gram has already done it: the grid only depends on the column maxima), F (n x B, ldf) is read only.
+// The digit planes of DH are rebuilt here rather than cached from the Gram: 1.5 ms per 2^20 points buys
+// independence from what happened to the buffer in between.
+int launch_project_i8(fps_ctx* ctx, float* DH, int64_t lda, const float* F, int64_t ldf, int B, int64_t n, double* R,
+                      int64_t ldr, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  GiState* s;
+  if (int rc = gi_state_get(ctx, &s)) return rc;
+  const int rows_b = (B + 63) / 64 * 64;
+  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : GI_MAX_CHUNK;
+  FPS_REQUIRE(max_chunk >= GI_SLAB && (max_chunk & (max_chunk - 1)) == 0, "FPS_GRAM_I8_CHUNK must be a power of two >= 128");
+  // Passes of max_chunk / 2^k points: pass boundaries nest inside the Gram's passes, so a pass never mixes rows that
+  // the Gram snapped on different grids (its column maxima can only be smaller -> a finer grid -> DH is unchanged).
+  int64_t chunk = max_chunk;
+  while ((size_t)GI_SL * rows_b * chunk > GI_B_PLANE_BYTES && chunk / 2 >= GI_SLAB) chunk /= 2;
+  if (chunk > n) chunk = n;
+  if (int rc = gi_reserve_planes(ctx, s->a, GI_ROWS, chunk)) return rc;
+  if (int rc = gi_reserve_planes(ctx, s->b, rows_b, chunk)) return rc;
+  s->a.rows = GI_ROWS;
+  s->b.rows = rows_b;
+  const bool have_cmax = ctx->dh_cmax_of == DH && ctx->dh_cmax_n == n;
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
+    const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
+    if (int rc = gi_split<true>(ctx, s->a, DH + p0 * lda, lda, np, FP, GI_ROWS, have_cmax ? ctx->dh_cmax : nullptr, st))
+      return rc;
+    if (int rc = gi_split<false>(ctx, s->b, const_cast<float*>(F) + p0 * ldf, ldf, np, B, rows_b, nullptr, st)) return rc;
+    if (int rc = gi_run(ctx, s, s->a, slabs, 0, s->b, slabs, slabs, false, FP, B, R, ldr, st)) return rc;
   }
   return 0;
 }

@@ -106,8 +106,11 @@ int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, co
 
 /* Replaces `RHSs @ f` (solver.py:197 + :301) for B right-hand sides at once:
  * R64 (FPS_FP, ldr) float64 += DH^T F,  DH (n, ld) float32,  F (n, ldf) float32, B columns.
- * Accumulating so that row shards / chunks can be summed; zero R64 first.                       */
-int fps_project_rhs(fps_ctx* ctx, const float* DH, int64_t n, int64_t ld, const float* F, int64_t ldf,
+ * Accumulating so that row shards / chunks can be summed; zero R64 first.
+ * For n >= 16384 and B >= 32 this runs on the int8 tensor cores with exact integer arithmetic like
+ * fps_gram_accum, on the same per-column grid of DH (DH is snapped in place - a no-op after
+ * fps_gram_accum) and on a private copy of F on a 31-bit grid per right-hand side.              */
+int fps_project_rhs(fps_ctx* ctx, float* DH, int64_t n, int64_t ld, const float* F, int64_t ldf,
                     int B, double* R64, int64_t ldr, void* stream);
 
 /* Replaces torch.linalg.solve + the bias formula (solver.py:305-306) for B right-hand sides:

@@ -161,7 +161,7 @@ def test_gram_int8_multipass_in_subprocess():
         torch.cuda.synchronize()
         R = A.double().T @ A.double()
         err = ((G - R).abs().max() / R.abs().max()).item()
-        assert err < 1e-14, err
+        assert err < 1e-13, err
         print("MULTIPASS_OK", err)
     """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.getcwd())
     env = dict(os.environ, FPS_GRAM_I8_CHUNK="8192")
