@@ -206,6 +206,7 @@ int fps_destroy(fps_ctx* ctx) {
   cudaSetDevice(ctx->device);
   tc_destroy(ctx);
   gram_i8_destroy(ctx);
+  recon_i8_destroy(ctx);
   for (int l = 0; l < NLAYER; ++l) {
     cudaFree(ctx->layer[l].w_hi);
     cudaFree(ctx->layer[l].w_lo);
@@ -379,11 +380,14 @@ int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64
   return launch_solve_factored(L64, R64, ldr, B, scale, s64, sum_bc64, nbc_total, W64, bias64, (cudaStream_t)stream);
 }
 
-int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
+int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
                     const double* bias64, int B, float* out, int64_t ldo, void* stream) {
   FPS_REQUIRE(ctx && A && W64 && out, "fps_reconstruct: null argument");
   FPS_REQUIRE(ldw >= B && ldo >= B, "fps_reconstruct: bad leading dimension");
   ProfScope ps(ctx, FPS_PROF_RECONSTRUCT, (cudaStream_t)stream);
+  static const int i8_min_b = getenv("FPS_RECON_I8_MIN_B") ? atoi(getenv("FPS_RECON_I8_MIN_B")) : 32;
+  if (use_i8(n) && B >= i8_min_b && ld >= FP && ld % 4 == 0 && (uintptr_t)A % 16 == 0)
+    return launch_recon_i8(ctx, A, ld, n, W64, ldw, bias64, B, out, ldo, (cudaStream_t)stream);
   return launch_reconstruct(ctx, A, n, ld, W64, ldw, bias64, B, out, ldo, (cudaStream_t)stream);
 }
 

@@ -80,6 +80,7 @@ struct fps_ctx {
   size_t workspace_bytes;
   void* tc_state;         // engine-private (tensor maps), owned by layer_tc.cu
   void* gi_state;         // int8 exact-Gram workspace, owned by gram_i8.cu (allocated on first use)
+  void* ri_state;         // int8 reconstruction workspace, owned by recon_i8.cu (allocated on first use)
   unsigned* dh_cmax;      // FPW words: per-feature max |DH| (float bits) of the last fps_features call (tcgen05 engine)
   const float* dh_cmax_of;  // the DH buffer those maxima describe (null: none), and its row count
   int64_t dh_cmax_n;
@@ -130,6 +131,10 @@ int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, in
 int launch_project_i8(fps_ctx* ctx, float* DH, int64_t lda, const float* F, int64_t ldf, int B, int64_t n, double* R,
                       int64_t ldr, cudaStream_t st);
 void gram_i8_destroy(fps_ctx* ctx);
+// out (n x B) = A W + bias on the int8 tensor cores with exact products (recon_i8.cu); snaps A in place
+int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double* W, int64_t ldw, const double* bias,
+                    int B, float* out, int64_t ldo, cudaStream_t st);
+void recon_i8_destroy(fps_ctx* ctx);
 int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st);
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
                            int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,

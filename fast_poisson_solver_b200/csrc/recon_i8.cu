@@ -1,0 +1,455 @@
+// Batched reconstruction  out[i, j] = sum_k A[i, k] W[k, j] + bias[j]   (solver.py:327-330 for B right-hand sides:
+// u = H w + b, f_pred = DH w) on the INT8 tensor cores with exact products.
+//
+// Why not fp32-grade tensor arithmetic: for rough sources |w| reaches 1e5 while u = O(1), the 700 terms cancel to
+// 1e-5 of their size, and the fp64-pipe kernel this replaces (28 TFLOP/s) exists for that reason.  Here:
+//   A (n x 704 fp32; H or DH)   X[i, k] = rint(A[i, k] 2^(30 - e_k)), e_k from the column maximum, four balanced
+//                               radix-256 digits; A is snapped in place to X 2^(e_k - 30) exactly like in
+//                               gram_i8.cu (a no-op for a DH that went through the Gram); digit planes
+//                               pa[d][i][k], feature axis contiguous = K-major, no transpose
+//   W (704 x B fp64)            W'[k, j] = W[k, j] 2^(e_k - 30) (exact), Y[k, j] = rint(W' 2^(38 - g_j)) with g_j from the
+//                               column maximum of W': a 39-bit integer, five digits; planes pw[d][j][k]
+//   out[i, j] = 2^(g_j - 38) sum_k X[i, k] Y[k, j] + bias[j],   X Y = sum_{a, b} 2^(8 (7 - a - b)) (Wd_a . Ad_b)
+// One tcgen05.mma.kind::i8 instruction multiplies one W digit (M = 256 right-hand sides per CTA pair) with the stack
+// of all four A digits of 64 points (N = 256) into the TMEM window that starts at column 64 a, so that column group
+// o collects the digit pairs with a + b = o (see gram_i8.cu).  K = 704 = 22 instructions of 32 per digit; the int32
+// accumulators cannot overflow (5 pairs x 704 x 2^14 < 2^26).  Orders 0..4 are combined in fp64 by the drain warps
+// (orders 5..7 weigh < 2^-40 of the largest term and are not read), scaled, biased and stored as fp32.
+// The rounding of W to 39 bits moves out by ~ sqrt(700) |w|_max 2^-39 |a|: 1e-9 of the largest term.
+#include "fps_common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace fps {
+
+constexpr int RI_TM = 128;                    // right-hand sides per CTA (UMMA M = 256 per pair)
+constexpr int RI_TN = 64;                     // points per tile
+constexpr int RI_DA = 4;                      // digits of A (stacked along UMMA N: 4 x 64 = 256)
+constexpr int RI_DW = 5;                      // digits of W
+constexpr int RI_NORD = 5;                    // digit orders read back (0..4)
+constexpr int RI_W_BYTES = RI_TM * 128;       // 16 KiB per W digit per 128-byte K slab
+constexpr int RI_A_BYTES = RI_TN * 128;       // 8 KiB per A digit per slab; a CTA stages two of the four
+constexpr int RI_STAGE = RI_DW * RI_W_BYTES + (RI_DA / 2) * RI_A_BYTES;  // 96 KiB
+constexpr int RI_STAGES = 2;
+constexpr int RI_SMEM = RI_STAGES * RI_STAGE + 1024 + 256;
+constexpr int RI_THREADS = 320;
+constexpr int RI_KSLABS = (FP + 127) / 128;   // 6 slabs, the last one holds 64 bytes (TMA zero-fills the rest)
+
+// ---- operand preparation ----------------------------------------------------------------------------
+// digits of A, K-major (no transpose): thread = 4 consecutive features of one point
+__global__ void __launch_bounds__(256)
+ri_split_a_kernel(float* __restrict__ A, int64_t ld, int64_t n, int64_t n_pad, const float2* __restrict__ scale,
+                  int8_t* __restrict__ planes) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = idx / (FP / 4);
+  const int k = (int)(idx % (FP / 4)) * 4;
+  if (i >= n_pad) return;
+  uint32_t word[RI_DA] = {0u, 0u, 0u, 0u};
+  if (i < n) {
+    float4 v = *reinterpret_cast<const float4*>(A + i * ld + k);
+    float vv[4] = {v.x, v.y, v.z, v.w};
+    bool changed = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 sc = scale[k + u];
+      int X = (k + u < F) ? __float2int_rn(vv[u] * sc.x) : 0;
+      const float snapped = (float)X * sc.y;
+      if (snapped != vv[u]) { vv[u] = snapped; changed = true; }
+#pragma unroll
+      for (int s = RI_DA - 1; s >= 1; --s) {
+        const int d = ((X + 128) & 255) - 128;
+        X = (X - d) >> 8;
+        word[s] |= (uint32_t)(d & 255) << (8 * u);
+      }
+      word[0] |= (uint32_t)(X & 255) << (8 * u);
+    }
+    if (changed) *reinterpret_cast<float4*>(A + i * ld + k) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  }
+#pragma unroll
+  for (int s = 0; s < RI_DA; ++s)
+    *reinterpret_cast<uint32_t*>(planes + ((int64_t)s * n_pad + i) * FP + k) = word[s];
+}
+
+// column maxima of W'[k, j] = W[k, j] 2^(e_k - 30) -> exponent g_j with |W'[:, j]| < 2^g_j
+__global__ void ri_wexp_kernel(const double* __restrict__ W, int64_t ldw, int B, int b_pad, const int* __restrict__ ea,
+                               int* __restrict__ gw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= b_pad) return;
+  int g = 0;
+  if (j < B) {
+    double m = 0.0;
+    for (int k = 0; k < F; ++k) m = fmax(m, fabs(ldexp(W[(int64_t)k * ldw + j], ea[k] - 30)));
+    if (m > 0.0) {
+      int ex;
+      frexp(m, &ex);   // m = f 2^ex, 0.5 <= f < 1  ->  m < 2^ex
+      g = ex;
+    }
+  }
+  gw[j] = g;
+}
+
+// digits of W', transposed to K-major: thread = (right-hand side j, 4 consecutive features)
+__global__ void __launch_bounds__(256)
+ri_split_w_kernel(const double* __restrict__ W, int64_t ldw, int B, int b_pad, const int* __restrict__ ea,
+                  const int* __restrict__ gw, int8_t* __restrict__ planes) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y * 4;
+  if (j >= b_pad) return;
+  uint32_t word[RI_DW] = {0u, 0u, 0u, 0u, 0u};
+  if (j < B) {
+    const int g = gw[j];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      long long Y = 0;
+      if (k + u < F) Y = __double2ll_rn(ldexp(W[(int64_t)(k + u) * ldw + j], ea[k + u] - 30 + 38 - g));
+#pragma unroll
+      for (int s = RI_DW - 1; s >= 1; --s) {
+        const long long d = ((Y + 128) & 255) - 128;
+        Y = (Y - d) >> 8;
+        word[s] |= (uint32_t)(d & 255) << (8 * u);
+      }
+      word[0] |= (uint32_t)(Y & 255) << (8 * u);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < RI_DW; ++s)
+    *reinterpret_cast<uint32_t*>(planes + ((int64_t)s * b_pad + j) * FP + k) = word[s];
+}
+
+// ---- the tensor-core kernel ---------------------------------------------------------------------------
+__device__ __forceinline__ void umma_i8_256(uint32_t tmem_d, uint64_t da, uint64_t db) {
+  constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void ri_tmem_ld16(uint32_t taddr, int* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void ri_tmem_zero16(uint32_t taddr) {
+  const int z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+
+struct RiParams {
+  float* out;            // (n, ldo) fp32
+  int64_t ldo;
+  int64_t n;             // valid points of this pass
+  int B;                 // valid right-hand sides
+  const int* gw;         // exponent per right-hand side
+  const double* bias;    // per right-hand side or null
+  int rhs_blocks;        // b_pad / 256
+  int point_blocks;      // n_pad / 64
+  int n_pad, b_pad;      // rows per digit plane of A / W
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RI_THREADS, 1)
+recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const RiParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + RI_STAGES * RI_STAGE;
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 32, bar_tfull = bar_base + 64, bar_tempty = bar_base + 72;
+  const uint32_t tmem_slot = bar_base + 80;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rank = (int)cluster_ctarank();
+  const int group = blockIdx.x / 2, ngroups = gridDim.x / 2;
+  const int ntiles = P.rhs_blocks * P.point_blocks;   // tile t: rhs block t % rhs_blocks, point block t / rhs_blocks
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    for (int s = 0; s < RI_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = group; t < ntiles; t += ngroups) {
+        const int jb = t % P.rhs_blocks, ib = t / P.rhs_blocks;
+        const int wrow = jb * 2 * RI_TM + rank * RI_TM, arow = ib * RI_TN;
+        for (int kb = 0; kb < RI_KSLABS; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * RI_STAGE;
+          const uint32_t full = bar_full + 8 * stage;
+          if (rank == 0) mbar_expect_tx(full, 2 * RI_STAGE);
+#pragma unroll
+          for (int s = 0; s < RI_DW; ++s) tma_load_2d<2>(sa + s * RI_W_BYTES, &tmW, full, kb * 128, s * P.b_pad + wrow);
+#pragma unroll
+          for (int s = 0; s < RI_DA / 2; ++s)   // stack rows [128 rank, 128 rank + 128) = A digits 2 rank, 2 rank + 1
+            tma_load_2d<2>(sa + RI_DW * RI_W_BYTES + s * RI_A_BYTES, &tmA, full, kb * 128, (2 * rank + s) * P.n_pad + arow);
+          if (++stage == RI_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (pair leader) =================
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int t = group; t < ntiles; t += ngroups) {
+        mbar_wait(bar_tempty, tphase);   // accumulators read and zeroed
+        tphase ^= 1;
+        tc_fence_after();
+        for (int kb = 0; kb < RI_KSLABS; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * RI_STAGE;
+          const uint64_t db = umma_desc<128>(sa + RI_DW * RI_W_BYTES);
+          const int ksteps = (kb == RI_KSLABS - 1) ? (FP - 128 * (RI_KSLABS - 1)) / 32 : 4;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t adv = (uint64_t)((j * 32) >> 4);
+#pragma unroll
+            for (int a = 0; a < RI_DW; ++a)
+              umma_i8_256(tmem_base + a * RI_TN, umma_desc<128>(sa + a * RI_W_BYTES) + adv, db + adv);
+          }
+          umma_commit<2>(bar_empty + 8 * stage);
+          if (++stage == RI_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<2>(bar_tfull);
+      }
+    }
+  } else {
+    // ================= drain warps 2..9 =================
+    const int quad = warp % 4;          // TMEM lanes [32 quad, 32 quad + 32) = right-hand sides
+    const int half = (warp - 2) / 4;    // 32 of the 64 points
+    const uint32_t taddr = tmem_base + half * (RI_TN / 2) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+    for (int o = 0; o < RI_DA + RI_DW - 1; ++o)
+#pragma unroll
+      for (int c = 0; c < RI_TN / 32; ++c) ri_tmem_zero16(taddr + o * RI_TN + c * 16);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(bar_tempty);
+    uint32_t tphase = 0;
+    for (int t = group; t < ntiles; t += ngroups) {
+      const int jb = t % P.rhs_blocks, ib = t / P.rhs_blocks;
+      const int j = jb * 2 * RI_TM + rank * RI_TM + quad * 32 + lane;
+      const bool j_ok = j < P.B;
+      const int g = j_ok ? P.gw[j] - 38 + 8 * (RI_DA + RI_DW - 2) : 0;   // out = 2^g sum_o 2^(-8 o) Acc_o
+      const double bj = (j_ok && P.bias) ? P.bias[j] : 0.0;
+      const int64_t i0 = (int64_t)ib * RI_TN + half * (RI_TN / 2);
+      mbar_wait(bar_tfull, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < RI_TN / 32; ++c) {
+        int v[RI_NORD][16];
+#pragma unroll
+        for (int o = 0; o < RI_NORD; ++o) ri_tmem_ld16(taddr + o * RI_TN + c * 16, v[o]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int o = 0; o < RI_DA + RI_DW - 1; ++o) ri_tmem_zero16(taddr + o * RI_TN + c * 16);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          double s = (double)v[RI_NORD - 1][q];
+#pragma unroll
+          for (int o = RI_NORD - 2; o >= 0; --o) s = fma(s, 0.00390625, (double)v[o][q]);
+          const int64_t i = i0 + c * 16 + q;
+          if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)(ldexp(s, g) + bj);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ri_colmax_kernel(const float* __restrict__ A, int64_t ld, int64_t n, int64_t rows_per_cta, unsigned* __restrict__ cmax) {
+  const int t = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+  const bool has2 = t + 512 < FP;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* row = A + r * ld;
+    m0 = fmaxf(m0, fabsf(__ldg(row + t)));
+    m1 = fmaxf(m1, fabsf(__ldg(row + t + 256)));
+    if (has2) m2 = fmaxf(m2, fabsf(__ldg(row + t + 512)));
+  }
+  atomicMax(cmax + t, __float_as_uint(m0));
+  atomicMax(cmax + t + 256, __float_as_uint(m1));
+  if (has2) atomicMax(cmax + t + 512, __float_as_uint(m2));
+}
+
+// same exponent / scale rule as gram_i8.cu (the grids must agree so that a snapped DH stays put)
+__global__ void ri_exps_kernel(const unsigned* __restrict__ cmax, int* __restrict__ exps, float2* __restrict__ scale) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= FPW) return;
+  int e = 0;
+  if (f < FP) {
+    const unsigned bits = cmax[f];
+    const int E = (int)(bits >> 23);
+    e = bits ? ((E > 0 ? E : 1) - 126) : 0;
+    if (e < -90) e = -90;
+  }
+  exps[f] = e;
+  scale[f] = make_float2(ldexpf(1.0f, 30 - e), ldexpf(1.0f, e - 30));
+}
+
+struct RiState {
+  int8_t* pa = nullptr;      // digit planes of A: RI_DA x n_pad x FP
+  size_t pa_bytes = 0;
+  int8_t* pw = nullptr;      // digit planes of W': RI_DW x b_pad x FP
+  size_t pw_bytes = 0;
+  unsigned* cmax = nullptr;  // FPW x {cmax, exps, scale}
+  int* exps = nullptr;
+  float2* scale = nullptr;
+  int* gw = nullptr;         // b_pad exponents
+  int gw_cap = 0;
+  void* encode = nullptr;
+};
+
+typedef CUresult (*RiEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void recon_i8_destroy(fps_ctx* ctx) {
+  RiState* s = static_cast<RiState*>(ctx->ri_state);
+  if (!s) return;
+  cudaFree(s->pa);
+  cudaFree(s->pw);
+  cudaFree(s->cmax);
+  cudaFree(s->gw);
+  delete s;
+  ctx->ri_state = nullptr;
+}
+
+static int ri_map(RiState* s, CUtensorMap* m, const int8_t* base, int64_t rows, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)FP, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)FP};
+  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((RiEncodeFn)s->encode)(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FPS_REQUIRE(r == CUDA_SUCCESS, "recon_i8: cuTensorMapEncodeTiled failed (%d), rows=%lld", (int)r, (long long)rows);
+  return 0;
+}
+
+constexpr int64_t RI_MAX_CHUNK = 1 << 20;   // points per pass: 2.75 GiB of digit planes
+
+// out (n x B, ldo) = A W + bias;  A (n x >= FP, lda) is snapped in place (see the header)
+int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double* W, int64_t ldw, const double* bias,
+                    int B, float* out, int64_t ldo, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  RiState* s = static_cast<RiState*>(ctx->ri_state);
+  if (!s) {
+    s = new RiState();
+    ctx->ri_state = s;
+    cudaDriverEntryPointQueryResult qres;
+    FPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &s->encode, cudaEnableDefault, &qres));
+    FPS_REQUIRE(s->encode && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    FPS_CUDA(cudaMalloc(&s->cmax, FPW * (sizeof(unsigned) + sizeof(int) + sizeof(float2))));
+    s->exps = reinterpret_cast<int*>(s->cmax + FPW);
+    s->scale = reinterpret_cast<float2*>(s->cmax + 2 * FPW);
+    FPS_CUDA(cudaFuncSetAttribute(recon_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RI_SMEM));
+  }
+  const int b_pad = (B + 2 * RI_TM - 1) / (2 * RI_TM) * (2 * RI_TM);
+  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : RI_MAX_CHUNK;
+  const int64_t chunk = n < max_chunk ? n : max_chunk;
+  const int64_t cap_pad = (chunk + RI_TN - 1) / RI_TN * RI_TN;
+  if ((size_t)RI_DA * cap_pad * FP > s->pa_bytes) {
+    if (s->pa) { FPS_CUDA(cudaFree(s->pa)); ctx->workspace_bytes -= s->pa_bytes; s->pa = nullptr; s->pa_bytes = 0; }
+    FPS_CUDA(cudaMalloc(&s->pa, (size_t)RI_DA * cap_pad * FP));
+    s->pa_bytes = (size_t)RI_DA * cap_pad * FP;
+    ctx->workspace_bytes += s->pa_bytes;
+  }
+  if ((size_t)RI_DW * b_pad * FP > s->pw_bytes) {
+    if (s->pw) { FPS_CUDA(cudaFree(s->pw)); ctx->workspace_bytes -= s->pw_bytes; s->pw = nullptr; s->pw_bytes = 0; }
+    FPS_CUDA(cudaMalloc(&s->pw, (size_t)RI_DW * b_pad * FP));
+    s->pw_bytes = (size_t)RI_DW * b_pad * FP;
+    ctx->workspace_bytes += s->pw_bytes;
+  }
+  if (b_pad > s->gw_cap) {
+    if (s->gw) FPS_CUDA(cudaFree(s->gw));
+    FPS_CUDA(cudaMalloc(&s->gw, (size_t)b_pad * sizeof(int)));
+    s->gw_cap = b_pad;
+  }
+  const bool have_cmax = ctx->dh_cmax_of == A && ctx->dh_cmax_n == n;
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
+    const int64_t n_pad = (np + RI_TN - 1) / RI_TN * RI_TN;
+    float* Ac = A + p0 * lda;
+    if (!have_cmax) {
+      FPS_CUDA(cudaMemsetAsync(s->cmax, 0, FPW * sizeof(unsigned), st));
+      int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (np + 31) / 32);
+      const int64_t rpc = (np + ctas - 1) / ctas;
+      ctas = (np + rpc - 1) / rpc;
+      ri_colmax_kernel<<<(unsigned)ctas, 256, 0, st>>>(Ac, lda, np, rpc, s->cmax);
+      count_launch(1);
+    }
+    ri_exps_kernel<<<(FPW + 255) / 256, 256, 0, st>>>(have_cmax ? ctx->dh_cmax : s->cmax, s->exps, s->scale);
+    {
+      const int64_t threads = n_pad * (FP / 4);
+      ri_split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Ac, lda, np, n_pad, s->scale, s->pa);
+    }
+    ri_wexp_kernel<<<(b_pad + 127) / 128, 128, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw);
+    ri_split_w_kernel<<<dim3((b_pad + 255) / 256, FP / 4), 256, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw, s->pw);
+    FPS_CUDA(cudaGetLastError());
+    CUtensorMap tmW, tmA;
+    if (ri_map(s, &tmW, s->pw, (int64_t)RI_DW * b_pad, RI_TM)) return 2;
+    if (ri_map(s, &tmA, s->pa, (int64_t)RI_DA * n_pad, RI_TN)) return 2;
+    RiParams P;
+    P.out = out + p0 * ldo;
+    P.ldo = ldo;
+    P.n = np;
+    P.B = B;
+    P.gw = s->gw;
+    P.bias = bias;
+    P.rhs_blocks = b_pad / (2 * RI_TM);
+    P.point_blocks = (int)(n_pad / RI_TN);
+    P.n_pad = (int)n_pad;
+    P.b_pad = b_pad;
+    const int pairs = ctx->sm_count / 2;
+    const int64_t ntiles = (int64_t)P.rhs_blocks * P.point_blocks;
+    const int groups = (int)std::min<int64_t>(ntiles, pairs);
+    recon_i8_kernel<<<groups * 2, RI_THREADS, RI_SMEM, st>>>(tmW, tmA, P);
+    FPS_CUDA(cudaGetLastError());
+    count_launch(5);
+  }
+  return 0;
+}
+
+}  // namespace fps

@@ -124,8 +124,11 @@ int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64
 
 /* Replaces the three GEMVs of solver.py:327-330 for B right-hand sides:
  *     out[i, j] = sum_k A[i, k] W[k, j] + (bias ? bias[j] : 0)       i < n, j < B
- * A (n, ld) float32 (H, DH or H_bc), W64 (FPS_FP, ldw) float64, out (n, ldo) float32.           */
-int fps_reconstruct(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
+ * A (n, ld) float32 (H, DH or H_bc), W64 (FPS_FP, ldw) float64, out (n, ldo) float32.
+ * For n >= 16384 and B >= 32 this runs on the int8 tensor cores with exact products (csrc/recon_i8.cu):
+ * A is snapped in place to the same per-column 31-bit grid as in fps_gram_accum (a no-op for a DH that
+ * went through it), W is used on a 39-bit grid per right-hand side.                             */
+int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
                     const double* bias64, int B, float* out, int64_t ldo, void* stream);
 
 /* Multi-lambda loss of solver.py:312-314 for one lambda: loss64[0] = mean((pred-ref)^2).        */

@@ -144,6 +144,52 @@ def test_gram_int8_exact_path(solver_factory):
         assert (A == A1).all() and (G2 == G).all()
 
 
+def test_project_and_reconstruct_int8_exact_paths(solver_factory):
+    """n >= 16384 and B >= 32: batched projection DH^T F and reconstruction A W + b run on the int8 tensor cores
+    (csrc/gram_i8.cu, csrc/recon_i8.cu) with exact integer products.  Checked against fp64 on the operands the kernels
+    define: DH / H snapped to their 31-bit column grids (in place), F on a 31-bit grid per right-hand side."""
+    from fast_poisson_solver_b200 import _lib
+
+    s = solver_factory()
+    lib, ctx, st = s._lib, s._ctx, s._stream()
+    rng = np.random.default_rng(9)
+    for n, B in ((16384, 32), (20001, 100), (33000, 700)):
+        x = torch.tensor(rng.uniform(0, 1, n), device="cuda")
+        y = torch.tensor(rng.uniform(0, 1, n), device="cuda")
+        H, DH = s._features(x, y, True)
+        G = torch.zeros((704, 704), dtype=torch.float64, device="cuda")
+        _lib.check(lib.fps_gram_accum(ctx, DH.data_ptr(), n, 704, G.data_ptr(), st), "gram")   # snaps DH
+        DH1 = DH.clone()
+        F = torch.tensor(rng.standard_normal((n, B)) * np.exp(rng.standard_normal((n, B))), dtype=torch.float32, device="cuda")
+        F0 = F.clone()
+        R = torch.zeros((704, B), dtype=torch.float64, device="cuda")
+        _lib.check(lib.fps_project_rhs(ctx, DH.data_ptr(), n, 704, F.data_ptr(), B, B, R.data_ptr(), B, st), "proj")
+        torch.cuda.synchronize()
+        assert (DH == DH1).all() and (F == F0).all()          # DH already on its grid, F never written
+        Fd = F.double()
+        e = (torch.floor(torch.log2(Fd.abs().max(0).values)) + 1).cpu().numpy().astype(int)
+        up = torch.tensor(np.ldexp(1.0, 30 - e), dtype=torch.float64, device="cuda")      # exact powers of two (a device
+        dn = torch.tensor(np.ldexp(1.0, e - 30), dtype=torch.float64, device="cuda")      # pow() is not: it flips ties)
+        Fg = torch.round(Fd * up[None, :]) * dn[None, :]
+        ref = DH.double().T @ Fg
+        scale = DH.double().norm(dim=0)[:, None] * Fg.norm(dim=0)[None, :]
+        assert ((R - ref).abs() / scale.clamp_min(1e-300))[:700].max().item() < 1e-13, (n, B)
+        assert ((R - DH.double().T @ Fd)[:700].norm() / ref[:700].norm()).item() < 1e-7   # vs the unrounded F
+        # reconstruction with heavily cancelling weights
+        W = torch.tensor(rng.standard_normal((704, B)) * 10.0 ** rng.uniform(0, 5, size=(704, 1)), dtype=torch.float64, device="cuda")
+        W[700:] = 0
+        bias = torch.tensor(rng.standard_normal(B), dtype=torch.float64, device="cuda")
+        for A in (H, DH):
+            out = torch.empty((n, B), dtype=torch.float32, device="cuda")
+            _lib.check(lib.fps_reconstruct(ctx, A.data_ptr(), n, 704, W.data_ptr(), B, bias.data_ptr(), B, out.data_ptr(), B, st), "recon")
+            torch.cuda.synchronize()
+            ref = A.double() @ W + bias[None]                 # A after the call = the snapped operand
+            terms = A.double().abs() @ W.abs()
+            err = (out.double() - ref).abs()
+            assert (err <= 6.0e-8 * ref.abs() + 2.0e-10 * terms + 1e-30).all(), (n, B, (err / terms).max().item())
+        assert (DH == DH1).all()
+
+
 def test_gram_int8_multipass_in_subprocess():
     """The chunk loop of the int8 Gram (n beyond one pass of digit planes), forced with FPS_GRAM_I8_CHUNK in a fresh process."""
     import subprocess, sys, textwrap
