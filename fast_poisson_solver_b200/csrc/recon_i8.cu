@@ -72,22 +72,30 @@ ri_split_a_kernel(float* __restrict__ A, int64_t ld, int64_t n, int64_t n_pad, c
     *reinterpret_cast<uint32_t*>(planes + ((int64_t)s * n_pad + i) * FP + k) = word[s];
 }
 
-// column maxima of W'[k, j] = W[k, j] 2^(e_k - 30) -> exponent g_j with |W'[:, j]| < 2^g_j
-__global__ void ri_wexp_kernel(const double* __restrict__ W, int64_t ldw, int B, int b_pad, const int* __restrict__ ea,
-                               int* __restrict__ gw) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= b_pad) return;
-  int g = 0;
-  if (j < B) {
-    double m = 0.0;
-    for (int k = 0; k < F; ++k) m = fmax(m, fabs(ldexp(W[(int64_t)k * ldw + j], ea[k] - 30)));
+// column maxima of W'[k, j] = W[k, j] 2^(e_k - 30) -> exponent g_j with |W'[:, j]| < 2^g_j.
+// Block = 32 right-hand sides x 8 feature groups (coalesced along j), reduced through shared memory.
+__global__ void __launch_bounds__(256)
+ri_wexp_kernel(const double* __restrict__ W, int64_t ldw, int B, int b_pad, const int* __restrict__ ea,
+               int* __restrict__ gw) {
+  __shared__ double sm[8][32];
+  const int jl = threadIdx.x % 32, kg = threadIdx.x / 32;
+  const int j = blockIdx.x * 32 + jl;
+  double m = 0.0;
+  if (j < B)
+    for (int k = kg; k < F; k += 8) m = fmax(m, fabs(W[(int64_t)k * ldw + j]) * __longlong_as_double((long long)(1023 + ea[k] - 30) << 52));
+  sm[kg][jl] = m;
+  __syncthreads();
+  if (kg == 0 && j < b_pad) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) m = fmax(m, sm[q][jl]);
+    int g = 0;
     if (m > 0.0) {
       int ex;
       frexp(m, &ex);   // m = f 2^ex, 0.5 <= f < 1  ->  m < 2^ex
       g = ex;
     }
+    gw[j] = g;
   }
-  gw[j] = g;
 }
 
 // digits of W', transposed to K-major: thread = (right-hand side j, 4 consecutive features)
@@ -256,7 +264,9 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const int jb = t % P.rhs_blocks, ib = t / P.rhs_blocks;
       const int j = jb * 2 * RI_TM + rank * RI_TM + quad * 32 + lane;
       const bool j_ok = j < P.B;
-      const int g = j_ok ? P.gw[j] - 38 + 8 * (RI_DA + RI_DW - 2) : 0;   // out = 2^g sum_o 2^(-8 o) Acc_o
+      // out = 2^g sum_o 2^(-8 o) Acc_o,  g = g_j - 38 + 56; 2^g as a double (|g| stays far inside the exponent range)
+      const int g = j_ok ? P.gw[j] - 38 + 8 * (RI_DA + RI_DW - 2) : 0;
+      const double scale = __longlong_as_double((long long)(1023 + g) << 52);
       const double bj = (j_ok && P.bias) ? P.bias[j] : 0.0;
       const int64_t i0 = (int64_t)ib * RI_TN + half * (RI_TN / 2);
       mbar_wait(bar_tfull, tphase);
@@ -276,7 +286,7 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
           for (int o = RI_NORD - 2; o >= 0; --o) s = fma(s, 0.00390625, (double)v[o][q]);
           const int64_t i = i0 + c * 16 + q;
-          if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)(ldexp(s, g) + bj);
+          if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)fma(s, scale, bj);
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -425,7 +435,7 @@ int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double
       const int64_t threads = n_pad * (FP / 4);
       ri_split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Ac, lda, np, n_pad, s->scale, s->pa);
     }
-    ri_wexp_kernel<<<(b_pad + 127) / 128, 128, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw);
+    ri_wexp_kernel<<<(b_pad + 31) / 32, 256, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw);
     ri_split_w_kernel<<<dim3((b_pad + 255) / 256, FP / 4), 256, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw, s->pw);
     FPS_CUDA(cudaGetLastError());
     CUtensorMap tmW, tmA;

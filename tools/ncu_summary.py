@@ -1,11 +1,14 @@
 """Summarise gpurun_out ncu artefacts into profiles/ (launch shares + key metrics of a full capture)."""
 import collections, csv, io, subprocess, sys
 
-def launch_shares(src, dst, header):
+def launch_shares(src, dst, header, only=None):
+    """only: substring a kernel name must contain (bench.py also runs torch.matmul peak measurements: not ours)."""
     lines = [l for l in open(src) if not l.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         k = row["Kernel Name"].split("(")[0]
+        if only and only not in row["Kernel Name"]:
+            continue
         a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += float(row["Metric Value"].replace(",", ""))
     tot = sum(a[1] for a in agg.values())
     out = header + ["kernel,launches,total_us,share_pct"]
