@@ -10,46 +10,100 @@
 
 namespace fps {
 
-constexpr int FOURIER_THREADS = 224;  // 200 frequency lanes + 8 pad lanes, rounded to warps
+constexpr int FOURIER_THREADS = 128;  // 100 frequency-pair lanes + 4 pad lanes, rounded to warps
 
+// sin and cos of a moderate fp64 argument (|z| < ~1e3 here: |z| <= |x F0| + |y F1| + |beta| ~ 40), branch free:
+// two-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on |r| <= pi/4 (~1 ulp in fp64; the
+// results are rounded to fp32 afterwards).  The library sincos() with its large-argument path cost three times
+// as many fp64 instructions and made this kernel compute bound.
+__device__ __forceinline__ void sincos_reduced(double z, double& sn, double& cs) {
+  const double kf = rint(z * 6.36619772367581382433e-01);           // z * 2/pi
+  const int q = (int)kf;
+  double r = fma(-kf, 1.57079632679489655800e+00, z);
+  r = fma(-kf, 6.12323399573676603587e-17, r);
+  const double r2 = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, r2, -2.50507602534068634195e-08);
+  ps = fma(ps, r2, 2.75573137070700676789e-06);
+  ps = fma(ps, r2, -1.98412698298579493134e-04);
+  ps = fma(ps, r2, 8.33333333332248946124e-03);
+  ps = fma(ps, r2, -1.66666666666666324348e-01);
+  const double s = fma(ps * r2, r, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, r2, 2.08757232129817482790e-09);
+  pc = fma(pc, r2, -2.75573143513906633035e-07);
+  pc = fma(pc, r2, 2.48015872894767294178e-05);
+  pc = fma(pc, r2, -1.38888888888741095749e-03);
+  pc = fma(pc, r2, 4.16666666666666019037e-02);
+  const double c = fma(pc * r2, r2, fma(-0.5, r2, 1.0));
+  const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;           // quadrant: (s, c), (c, -s), (-s, -c), (-c, s)
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+
+// two adjacent columns at once (idx even): 4-byte stores into the fp16 planes, 8-byte into the fp32 planes
+__device__ __forceinline__ void store_planes2(const ActPlanes& P, size_t idx, float v0, float v1, float scale) {
+  if (P.f16) {
+    const float t0 = v0 * scale, t1 = v1 * scale;
+    const __half2 h = __floats2half2_rn(t0, t1);
+    const float2 hf = __half22float2(h);
+    *reinterpret_cast<__half2*>(P.hi16 + idx) = h;
+    *reinterpret_cast<__half2*>(P.lo16 + idx) = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+  } else {
+    const float h0 = tf32_hi(v0), h1 = tf32_hi(v1);
+    *reinterpret_cast<float2*>(P.hi + idx) = make_float2(h0, h1);
+    *reinterpret_cast<float2*>(P.lo + idx) = make_float2(v0 - h0, v1 - h1);
+  }
+}
+
+// Thread j2 < 100 owns the frequency pair (2 j2, 2 j2 + 1); threads 100..103 zero the K padding (columns
+// 400..415).  The kernel is bound by its stores (6.6 KB per point in 2-byte elements): pairing the columns
+// halves the store instructions.
 template <int S>
 __global__ void __launch_bounds__(FOURIER_THREADS)
 fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
                const double* __restrict__ ffm, const ActPlanes P, const StreamScale sc) {
-  const int j = threadIdx.x;
-  double f0 = 0, f1 = 0, c = 0, beta = 0;
+  const int j = 2 * threadIdx.x;
+  double f0[2] = {0, 0}, f1[2] = {0, 0}, c[2] = {0, 0}, beta[2] = {0, 0}, k2[2];
   if (j < NFREQ) {
-    f0 = ffm[j];
-    f1 = ffm[NFREQ + j];
-    c = ffm[2 * NFREQ + j];
-    beta = ffm[3 * NFREQ + j];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      f0[u] = ffm[j + u];
+      f1[u] = ffm[NFREQ + j + u];
+      c[u] = ffm[2 * NFREQ + j + u];
+      beta[u] = ffm[3 * NFREQ + j + u];
+    }
   }
-  const double k2 = f0 * f0 + f1 * f1;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) k2[u] = f0[u] * f0[u] + f1[u] * f1[u];
   for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
     const size_t row = (size_t)p * S * K0P;
     if (j < NFREQ) {
-      const double z = fma(x[p], f0, fma(y[p], f1, beta));
-      double sn, cs;
-      sincos(z, &sn, &cs);
-      sn *= c;
-      cs *= c;
-      store_planes(P, row + j, (float)sn, sc.s[0]);
-      store_planes(P, row + NFREQ + j, (float)cs, sc.s[0]);
+      const double xp = x[p], yp = y[p];
+      double sn[2], cs[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        sincos_reduced(fma(xp, f0[u], fma(yp, f1[u], beta[u])), sn[u], cs[u]);
+        sn[u] *= c[u];
+        cs[u] *= c[u];
+      }
+      store_planes2(P, row + j, (float)sn[0], (float)sn[1], sc.s[0]);
+      store_planes2(P, row + NFREQ + j, (float)cs[0], (float)cs[1], sc.s[0]);
       if (S == 4) {
-        store_planes(P, row + K0P + j, (float)(cs * f0), sc.s[1]);
-        store_planes(P, row + K0P + NFREQ + j, (float)(-sn * f0), sc.s[1]);
-        store_planes(P, row + 2 * K0P + j, (float)(cs * f1), sc.s[2]);
-        store_planes(P, row + 2 * K0P + NFREQ + j, (float)(-sn * f1), sc.s[2]);
-        store_planes(P, row + 3 * K0P + j, (float)(-k2 * sn), sc.s[3]);
-        store_planes(P, row + 3 * K0P + NFREQ + j, (float)(-k2 * cs), sc.s[3]);
+        store_planes2(P, row + K0P + j, (float)(cs[0] * f0[0]), (float)(cs[1] * f0[1]), sc.s[1]);
+        store_planes2(P, row + K0P + NFREQ + j, (float)(-sn[0] * f0[0]), (float)(-sn[1] * f0[1]), sc.s[1]);
+        store_planes2(P, row + 2 * K0P + j, (float)(cs[0] * f1[0]), (float)(cs[1] * f1[1]), sc.s[2]);
+        store_planes2(P, row + 2 * K0P + NFREQ + j, (float)(-sn[0] * f1[0]), (float)(-sn[1] * f1[1]), sc.s[2]);
+        store_planes2(P, row + 3 * K0P + j, (float)(-k2[0] * sn[0]), (float)(-k2[1] * sn[1]), sc.s[3]);
+        store_planes2(P, row + 3 * K0P + NFREQ + j, (float)(-k2[0] * cs[0]), (float)(-k2[1] * cs[1]), sc.s[3]);
       }
     } else if (j < NFREQ + 8) {
-      // zero the K padding (columns 400..415) of every stream row
+      // zero the K padding (columns 400..415) of every stream row: 4 threads x 4 columns
       const int c0 = K0 + 2 * (j - NFREQ);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        store_planes(P, row + s * K0P + c0, 0.f, 1.f);
-        store_planes(P, row + s * K0P + c0 + 1, 0.f, 1.f);
+        store_planes2(P, row + s * K0P + c0, 0.f, 0.f, 1.f);
+        store_planes2(P, row + s * K0P + c0 + 2, 0.f, 0.f, 1.f);
       }
     }
   }
@@ -58,7 +112,7 @@ fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64
 int launch_fourier(const fps_ctx* ctx, const double* x, const double* y, int64_t n, int streams, ActPlanes out,
                    cudaStream_t st) {
   if (n <= 0) return 0;
-  int64_t blocks = n < (int64_t)ctx->sm_count * 8 ? n : (int64_t)ctx->sm_count * 8;
+  int64_t blocks = n < (int64_t)ctx->sm_count * 16 ? n : (int64_t)ctx->sm_count * 16;
   if (streams == 4)
     fourier_kernel<4><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0]);
   else

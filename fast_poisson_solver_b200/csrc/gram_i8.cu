@@ -47,13 +47,13 @@ constexpr int GI_ROWS = FPW;                // 768 feature rows per digit plane
 constexpr int GI_RING = 220 * 1024;
 constexpr int GI_SMEM = GI_RING + 1024 + 256;
 constexpr int GI_THREADS = 320;             // TMA warp, MMA warp, 8 drain warps
-constexpr int GI_NTILES = 24;               // (256 x 64) tiles that touch the lower triangle of 768 x 768
+constexpr int GI_NTILES = 23;               // (256 x 64) tiles that touch the lower triangle of 704 x 704 (padded to 768 rows)
 // points per TMEM drain: an order holds at most 4 digit pairs of magnitude <= 2^14 -> 2^16 per point;
 // 28 672 points keep every accumulator below 2^31
 constexpr int GI_SEG_POINTS = 28672;
 constexpr int GI_TILE_ELEMS = 2 * GI_TM * GI_TN;  // fp64 partial tile of a pair
 
-// row block I (256 features) needs the column blocks J (64 features) with 64 J <= 256 I + 255: 4 + 8 + 12
+// row block I (256 features) needs the column blocks J (64 features) with 64 J <= 256 I + 255 and 64 J < 704: 4 + 8 + 11
 __host__ __device__ inline void gi_tile(int t, int& I, int& J) {
   if (t < 4) { I = 0; J = t; }
   else if (t < 12) { I = 1; J = t - 4; }
@@ -120,17 +120,23 @@ gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int row
   const bool col_ok = f < ncols;
   const float sc = scale[f].x, inv_sc = scale[f].y;   // powers of two: both products below are exact
   const int64_t pbase = (int64_t)blockIdx.x * GI_SLAB + pq * 32;
+  // all 32 loads first: the in-place stores below would otherwise serialise them (same array)
+  float vals[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int64_t p = pbase + q;
+    vals[q] = (col_ok && p < n) ? A[p * ld + f] : 0.f;
+  }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     uint32_t word[GI_SL] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int64_t p = pbase + it * 4 + u;
-      const float v = (col_ok && p < n) ? A[p * ld + f] : 0.f;
+      const float v = vals[it * 4 + u];
       int X = __float2int_rn(v * sc);
       if (SNAP) {
         const float snapped = (float)X * inv_sc;   // exact: X has at most 24 significant bits
-        if (snapped != v) A[p * ld + f] = snapped;
+        if (snapped != v) A[(pbase + it * 4 + u) * ld + f] = snapped;
       }
 #pragma unroll
       for (int s = GI_SL - 1; s >= 1; --s) {
