@@ -195,6 +195,8 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   ctx->partial_bytes = (size_t)1024 * 64 * 64 * sizeof(double);  // 32 MiB of split-K tiles
   FPS_CUDA(cudaMalloc(&ctx->partial, ctx->partial_bytes));
   FPS_CUDA(cudaMalloc(&ctx->dh_cmax, FPW * sizeof(unsigned)));
+  FPS_CUDA(cudaMalloc(&ctx->tc_sched, 2 * sizeof(int)));
+  FPS_CUDA(cudaMemset(ctx->tc_sched, 0, 2 * sizeof(int)));
   ctx->workspace_bytes = 4 * plane + ctx->partial_bytes;
   if (tc_init(ctx)) { fps_destroy(ctx); return 3; }
   *out = ctx;
@@ -222,6 +224,7 @@ int fps_destroy(fps_ctx* ctx) {
   }
   cudaFree(ctx->partial);
   cudaFree(ctx->dh_cmax);
+  cudaFree(ctx->tc_sched);
   delete ctx->prof;
   delete ctx;
   return 0;

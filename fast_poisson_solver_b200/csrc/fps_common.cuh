@@ -79,6 +79,7 @@ struct fps_ctx {
   size_t partial_bytes;
   size_t workspace_bytes;
   void* tc_state;         // engine-private (tensor maps), owned by layer_tc.cu
+  int* tc_sched;          // 2 ints for the dynamic tile scheduler of layer_tc_pair_kernel (zero between launches)
   void* gi_state;         // int8 exact-Gram workspace, owned by gram_i8.cu (allocated on first use)
   void* ri_state;         // int8 reconstruction workspace, owned by recon_i8.cu (allocated on first use)
   unsigned* dh_cmax;      // FPW words: per-feature max |DH| (float bits) of the last fps_features call (tcgen05 engine)

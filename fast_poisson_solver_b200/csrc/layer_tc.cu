@@ -119,6 +119,7 @@ struct TcParams {
   float gain;      // 1 + kappa(K_seg): first-order compensation of the accumulator truncation bias
   float gain_tail; // same for the shorter last segment of a tile
   int stages;      // ring depth actually used (<= RING_BYTES / stage bytes)
+  int* sched;      // pair kernel: {next tile, finished pairs} for the dynamic tile scheduler (both zero between launches)
 };
 
 // F16 = false: 3xTF32, planes hi32 / lo32, K slab = 16 floats.  F16 = true: FP16x2 split, planes hi16 / lo16,
@@ -142,6 +143,9 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
   // barrier slots (8 bytes each): full[8], empty[8], tmem_full[2], tmem_empty[2], then the TMEM base word
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 64, bar_tfull = bar_base + 128, bar_tempty = bar_base + 144;
   const uint32_t tmem_slot = bar_base + 160;
+  // dynamic tile scheduler (pairs): sched_full[4] | sched_empty[4] (leader's copy is used) | tile ids[4]
+  constexpr int SQ = 4;
+  const uint32_t sched_full = bar_base + 176, sched_empty = bar_base + 208, sched_tile = bar_base + 240;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -164,6 +168,10 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
       mbar_init(bar_tfull + 8 * s, 1);
       mbar_init(bar_tempty + 8 * s, 8 * NCTA);  // one arrive per accumulate warp of every CTA in the pair
     }
+    for (int s = 0; s < SQ; ++s) {
+      mbar_init(sched_full + 8 * s, 1);
+      mbar_init(sched_empty + 8 * s, 18);       // leader: MMA issuer + 8 warps; peer: producer + 8 warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -182,11 +190,58 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // ---- tile sequence of this CTA (pair) --------------------------------------------------------------------
+  // NCTA == 1: static round robin.  NCTA == 2: DYNAMIC.  SMs differ by ~10 % in operand-feed rate (L2 die
+  // locality), so equal static shares left the fast pairs idle for the last ~9 % of every launch.  The leader's
+  // producer thread draws tile numbers from a global counter and publishes them through a 4-deep queue in the
+  // shared memory of both CTAs; every other role (peer producer, MMA issuer, the 16 accumulate warps) reads the
+  // queue in order.  -1 ends the sequence.  The last pair to finish resets the counter for the next launch.
+  uint32_t sq_slot = 0, sq_phase = 0;
+  int t_static = group - ngroups;
+  auto sq_advance = [&]() { if (++sq_slot == SQ) { sq_slot = 0; sq_phase ^= 1; } };
+  // leader producer thread only: `ticket` = a number drawn from the global counter (drawn one tile ahead, so that
+  // the latency of the atomic hides behind the loads of the current tile)
+  auto draw_ticket = [&]() -> int { return (NCTA == 1) ? 0 : atomicAdd(P.sched, 1); };
+  auto publish_tile = [&](int ticket) -> int {
+    if (NCTA == 1) { t_static += ngroups; return t_static < total_tiles ? t_static : -1; }
+    mbar_wait(sched_empty + 8 * sq_slot, sq_phase ^ 1);
+    const int t = ticket < total_tiles ? ticket : -1;
+#pragma unroll
+    for (uint32_t r = 0; r < 2; ++r) st_cluster_u32(mapa_u32(sched_tile + 4 * sq_slot, r), (uint32_t)t);
+#pragma unroll
+    for (uint32_t r = 0; r < 2; ++r) mbar_arrive_release_cluster(mapa_u32(sched_full + 8 * sq_slot, r));
+    sq_advance();
+    if (t < 0 && atomicAdd(P.sched + 1, 1) == ngroups - 1) {   // every pair has drawn its last ticket
+      P.sched[0] = 0;
+      P.sched[1] = 0;
+    }
+    return t;
+  };
+  auto next_tile_thread = [&]() -> int {       // a single consumer thread (peer producer, MMA issuer)
+    if (NCTA == 1) { t_static += ngroups; return t_static < total_tiles ? t_static : -1; }
+    mbar_wait_cluster(sched_full + 8 * sq_slot, sq_phase);
+    const int t = (int)ld_shared_u32(sched_tile + 4 * sq_slot);
+    if (t >= -1) mbar_arrive_leader(sched_empty + 8 * sq_slot);   // (always true: orders the read before the arrive)
+    sq_advance();
+    return t;
+  };
+  auto next_tile_warp = [&]() -> int {         // a whole consumer warp
+    if (NCTA == 1) { t_static += ngroups; return t_static < total_tiles ? t_static : -1; }
+    mbar_wait_cluster(sched_full + 8 * sq_slot, sq_phase);
+    const int t = (int)ld_shared_u32(sched_tile + 4 * sq_slot);
+    __syncwarp();
+    if (lane == 0 && t >= -1) mbar_arrive_leader(sched_empty + 8 * sq_slot);
+    sq_advance();
+    return t;
+  };
+
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = group; t < total_tiles; t += ngroups) {
+      int t = (rank == 0) ? publish_tile(draw_ticket()) : next_tile_thread();
+      while (t >= 0) {
+        const int ticket = (rank == 0) ? draw_ticket() : 0;
         const int ft = (t % FT_GROUPS) * NCTA + rank, rt = t / FT_GROUPS;
         const int brow = rt * TN + rank * (TN / NCTA);
         for (int kc = 0; kc < P.nk; ++kc) {
@@ -205,6 +260,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        t = (rank == 0) ? publish_tile(ticket) : next_tile_thread();
       }
     }
   } else if (warp == 1) {
@@ -212,7 +268,9 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
       const long long t_loop = clock64();
-      for (int t = group; t < total_tiles; t += ngroups) {
+      for (;;) {
+        const int t = next_tile_thread();
+        if (t < 0) break;
         TC_STAT_ADD(6, 1);
         for (int kc0 = 0; kc0 < P.nk; kc0 += P.seg) {
           const int kc1 = (kc0 + P.seg < P.nk) ? kc0 + P.seg : P.nk;
@@ -265,7 +323,9 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
     const int quad = warp % 4;          // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
     const int half = (warp - 2) / 4;    // which 128 of the 256 accumulator columns
     uint32_t abuf = 0, aphase = 0;
-    for (int t = group; t < total_tiles; t += ngroups) {
+    for (;;) {
+      const int t = next_tile_warp();
+      if (t < 0) break;
       const int ft = (t % FT_GROUPS) * NCTA + rank, rt = t / FT_GROUPS;
       const int f = ft * TM + quad * 32 + lane;  // this thread's output feature
 
@@ -502,6 +562,7 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.H = H;
   P.DH = DH;
   P.dh_cmax = (last && DH) ? ctx->dh_cmax : nullptr;
+  P.sched = ctx->tc_sched;
   P.ld = ld;
   P.rows = points * streams;
   const bool wide = f16 && s->pair && s->rb == 128;     // 128-byte slab rows (SWIZZLE_128B)
