@@ -391,11 +391,12 @@ def run_ours(args):
                                     "fp32-grade products need 3 MMAs each and M is padded 700->768, so frac cannot "
                                     "exceed frac_ceiling; issued_frac is the tensor-pipe share actually occupied",
                      "launches": int(hid_n), "avg_launch_ms": hid_ms / hid_n if hid_n else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one 18 944-point launch, ncu --set full,
-                     # profiles/r01b_layer_tc_ncu_full_summary.csv (algorithmic: 427 MB in + 424 MB out + 4 MB weights)
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one 18 944-point launch (ncu --set full,
-                     # profiles/r01c_layer_tc_ncu_full_summary.csv); algorithmic: 213 MB in + 212 MB out + 2 MB weights
-                     "traffic": 388.8e6 if f16_fmt else 846.7e6, "traffic_unit": "bytes/launch (ncu)"},
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
+                     # (profiles/r01d_layer_tc_ncu_full_summary.csv: 390.8 MB for an 18 944-point launch = 20.6 KB per
+                     # point; algorithmic: 11.3 KB in + 11.3 KB out per point + 2 MB of weights), scaled to the points
+                     # of one launch of this run
+                     "traffic": (20.6e3 if f16_fmt else 44.7e3) * (4 * args.steps * n_pts / hid_n) if hid_n else None,
+                     "traffic_unit": "bytes/launch (ncu, per-point figure x points per launch)"},
         "other_rooflines": {
             "features_all_layers": {"achieved": n_pts * FLOP_PER_POINT_FEATURES / (feat_ms * 1e-3) / 1e12,
                                     "peak": tc_peak, "unit": "TFLOP/s (algorithmic, 3 MMAs issued per product)"},

@@ -167,7 +167,8 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
     ctx->act_scale[l].s[3] = 1.f / 16.f;
   }
   // default wave: 296 row tiles x 6 feature tiles = 1776 = 12 x 148 CTA tiles (no tail wave on B200)
-  ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 18944;
+  // default wave: 37 888 points (1.7 GB of activation planes); fewer, longer launches than the earlier 18 944
+  ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 37888;
   int rc = upload_layer(ctx->layer[0], w->h_w0, w->h_b0, K0, K0P);
   for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer(ctx->layer[l + 1], w->h_wh[l], w->h_bh[l], F, FP);
   if (rc == 0) rc = upload_layer_f64(ctx, 0, w->h_w0, w->h_b0, K0, K0P);
@@ -237,7 +238,8 @@ int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t
   const int64_t np = n < 512 ? n : 512;
   unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->partial);  // NLAYER x 4 words of scratch
   FPS_CUDA(cudaMemsetAsync(d_max, 0, NLAYER * 4 * sizeof(unsigned int), st));
-  // run the sample through the fp32 cross-check engine with TF32-format planes and look at every layer input
+  // run the sample through the scale-free TF32-format planes (3xTF32 tensor-core kernel, or the fp32 cross-check
+  // engine when that is the selected one) and look at every layer input
   const int f16_saved = ctx->f16;
   ctx->f16 = 0;
   for (int i = 0; i < 2; ++i) ctx->act[i].f16 = 0;
@@ -247,7 +249,9 @@ int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t
     plane_absmax_kernel<4><<<512, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, K, d_max + 4 * l);
     count_launch();
     if (l < NLAYER - 1) {
-      rc = launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st);
+      rc = (ctx->engine == FPS_ENGINE_TCGEN05)
+               ? launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st)
+               : launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st);
       cur ^= 1;
     }
   }
