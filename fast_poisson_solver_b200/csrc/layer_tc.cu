@@ -1,38 +1,38 @@
-// Dense layer + tanh with forward-mode derivative streams on the 5th-gen tensor cores
-// (FPS_ENGINE_TCGEN05): TMA -> swizzled shared memory -> tcgen05.mma.kind::tf32 (3xTF32 split)
+// Dense layer + tanh with forward-mode derivative streams on the 5th-gen tensor cores (FPS_ENGINE_TCGEN05):
+// TMA -> 128B-swizzled shared memory -> tcgen05.mma.kind::f16 (FP16x2 split, three MMAs per product)
 // -> fp32 segment accumulators in TMEM -> tcgen05.ld -> round-to-nearest running sums in registers
 // -> fused tanh/derivative epilogue -> next layer's hi/lo planes (or H / DH for the last layer).
 //
 // Reference maths: nn.Linear + nn.Tanh (model.py:53-60, :144) and the Laplacian that
 // utils.py:54-68 extracts by 2 800 autograd sweeps, here as closed-form streams.
 //
-// GEMM mapping (per CTA):
-//   D[f, r] = sum_k W[f, k] * Act[r, k]      f: 128 output features  -> UMMA M  (TMEM lanes)
+// GEMM mapping (per CTA pair, cta_group::2):
+//   D[f, r] = sum_k W[f, k] * Act[r, k]      f: 256 output features  -> UMMA M  (128 TMEM lanes per CTA)
 //                                            r: 256 activation rows  -> UMMA N  (TMEM columns)
-//   A operand = W tile   (128 x TK fp32, K-major, swizzled)  hi and lo planes
-//   B operand = Act tile (256 x TK fp32, K-major, swizzled)  hi and lo planes
+//   A operand = W tile   (128 x 64 halves per CTA, K-major, SWIZZLE_128B)  hi and lo planes
+//   B operand = Act tile (256 x 64 halves, 128 rows staged by each CTA)    hi and lo planes
 //   Activation row r = 4*point + stream, so one thread (= one TMEM lane = one feature) finds the
 //   four streams (v, v_x, v_y, v_lap) of a point in four adjacent TMEM columns and can apply the
 //   tanh recurrences without any cross-thread exchange.
-//   3xTF32:  D += Alo*Bhi + Ahi*Blo + Ahi*Bhi per 8-wide k step (hi = fp32 with the low 13 mantissa
-//   bits cleared, lo = exact remainder; both planes are produced by the previous layer's epilogue).
+//   Products:  D += Alo*Bhi + Ahi*Blo + Ahi*Bhi per 16-wide k step on fp16 planes of power-of-two scaled
+//   values (hi = fp16(v S), lo = fp16(v S - hi); fps_common.cuh).  Template parameter F16 = false selects
+//   the earlier 3xTF32 format (fp32 planes, kind::tf32, 8-wide k steps); it also serves the scale calibration,
+//   which needs a scale-free format.  RB = bytes of K per shared-memory row (64 or 128; 128 in production).
 //
-// NCTA = 2 (production): two CTAs of a cluster form a tcgen05 pair (cta_group::2, UMMA M = 256).
-//   CTA rank r owns feature tile 2*fp + r; the 256-row activation tile is SHARED: each CTA loads only
-//   128 of its rows and the tensor cores of both SMs read both halves.  That cuts the L2->SM operand
-//   traffic per MMA by a third (64 instead of 96 KiB per K=32), which is what bounds this kernel
-//   (measured: with 1-CTA tiles the tensor pipe sits at 60 % while L2->SM runs at 8.7 TB/s).
+// The pair shares the 256-row activation tile: each CTA loads only 128 of its rows and the tensor cores of
+// both SMs read both halves.  That cut the L2->SM operand traffic per MMA by a third, which bounds this kernel.
 // NCTA = 1: single-CTA variant kept for A/B measurements (FPS_TC_PAIR=0).
 //
 // Accumulation accuracy.  The tensor core truncates (rounds toward zero) when it writes the fp32
-// accumulator, so a single 704-long chain of 264 MMAs biases every output by ~3e-6 per layer
-// (measured: H off by 1.6e-5 after six layers).  The K loop is therefore cut into segments of 32:
-// each segment accumulates in TMEM from zero, then the accumulate warps pull it out with tcgen05.ld
-// and add it to a round-to-nearest fp32 running sum held in registers while the tensor core already
-// works on the next segment in the other TMEM buffer.
+// accumulator, so a single 704-long chain biases every output by ~3e-6 per layer (measured: H off by 1.6e-5
+// after six layers).  The K loop is therefore cut into segments (K = 192): each segment accumulates in TMEM
+// from zero, then the accumulate warps pull it out with tcgen05.ld and add it, times a gain 1 + kappa(K_seg)
+// that compensates the first-order shrink, to a round-to-nearest fp32 running sum held in registers while the
+// tensor core already works on the next segment in the other TMEM buffer.
 //
 // Warp roles (320 threads, persistent CTAs, one per SM):
-//   warp 0     TMA producer (ring of {Ahi, Alo, Bhi, Blo} K=16 slabs; 4 stages x 48 KiB or 6 x 32 KiB)
+//   warp 0     TMA producer (ring of {Ahi, Alo, Bhi, Blo} slabs: 3 stages x 64 KiB); in the pair leader also the
+//              tile scheduler (dynamic: a global ticket counter, see "tile sequence" below)
 //   warp 1     TMEM allocator + MMA issuer (one elected lane; in a pair only the rank-0 CTA issues)
 //   warps 2-9  accumulate + epilogue; TMEM lane quadrant = warp_id % 4, column half = (warp_id-2)/4,
 //              128 running sums per thread.  The 512 TMEM columns hold two 256-column segment
