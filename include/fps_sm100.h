@@ -84,7 +84,10 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n,
  * (csrc/gram_i8.cu).  That path SNAPS A IN PLACE to a per-column 31-bit fixed-point grid: elements
  * below 2^-7 of their column maximum move by less than 2^-31 of that maximum (under 1 % of one
  * fp32 ulp of the maximum), all others are unchanged, and G64 receives the Gram of the stored A
- * to fp64 rounding.  Call it before anything else consumes A (fps_project_rhs, fps_reconstruct). */
+ * to fp64 rounding.  Call it before anything else consumes A (fps_project_rhs, fps_reconstruct).
+ * When A is the DH buffer of the latest fps_features call on this context (same pointer, same n),
+ * the column maxima recorded by that call are used instead of a separate pass over A: do not
+ * modify the buffer between the two calls.                                                      */
 int fps_gram_accum(fps_ctx* ctx, float* A, int64_t n, int64_t ld, double* G64, void* stream);
 
 /* Replaces `Ht_bc @ ones` (solver.py:176-178): s64 (FPS_FP) float64 += column sums of A.        */
