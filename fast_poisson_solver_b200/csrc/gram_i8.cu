@@ -110,16 +110,21 @@ __global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int ncols, int
 // rows = feature rows per digit plane (a multiple of 64 >= ncols); columns >= ncols produce zero digits.
 template <bool SNAP>
 __global__ void __launch_bounds__(256)
-gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int rows, const float2* __restrict__ scale,
-                int8_t* __restrict__ planes) {
+gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int rows, int slabs,
+                const float2* __restrict__ scale, int8_t* __restrict__ planes) {
   __shared__ uint32_t sm[GI_SL][64][33];
   const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int fh = w & 1, pq = w >> 1;
   const int fl = fh * 32 + lane;
-  const int f = blockIdx.y * 64 + fl;
+  // feature block = blockIdx.x (fastest varying): the CTAs that share a slab's rows run together, so each
+  // 128-row band of A is read as whole rows by neighbouring CTAs (DRAM page locality); slab = blockIdx.y + 65535 z
+  const int fb = blockIdx.x;
+  const int64_t slab_idx = (int64_t)blockIdx.z * 65535 + blockIdx.y;
+  const int f = fb * 64 + fl;
   const bool col_ok = f < ncols;
+  if (slab_idx >= slabs) return;   // (whole CTA: before the barrier)
   const float sc = scale[f].x, inv_sc = scale[f].y;   // powers of two: both products below are exact
-  const int64_t pbase = (int64_t)blockIdx.x * GI_SLAB + pq * 32;
+  const int64_t pbase = slab_idx * GI_SLAB + pq * 32;
   // all 32 loads first: the in-place stores below would otherwise serialise them (same array)
   float vals[32];
 #pragma unroll
@@ -151,12 +156,12 @@ gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int row
   }
   __syncthreads();
   // planes[slab][digit][feature][128]: a (digit, 64-feature) group is 8 KiB of consecutive bytes
-  int8_t* slab = planes + (int64_t)blockIdx.x * ((int64_t)GI_SL * rows * GI_SLAB);
+  int8_t* slab = planes + slab_idx * ((int64_t)GI_SL * rows * GI_SLAB);
 #pragma unroll 4
   for (int rr = 0; rr < 32; ++rr) {
     const int row = w * 32 + rr;
     const int s = row / 64, rfl = row % 64;
-    *reinterpret_cast<uint32_t*>(slab + ((int64_t)s * rows + blockIdx.y * 64 + rfl) * GI_SLAB + lane * 4) = sm[s][rfl][lane];
+    *reinterpret_cast<uint32_t*>(slab + ((int64_t)s * rows + fb * 64 + rfl) * GI_SLAB + lane * 4) = sm[s][rfl][lane];
   }
 }
 
@@ -489,8 +494,10 @@ static int gi_split(fps_ctx* ctx, GiPlanes& pl, float* A, int64_t lda, int64_t n
   }
   gi_exps_kernel<<<(rows + 255) / 256, 256, 0, st>>>(known ? known : pl.cmax, ncols, rows, pl.exps, pl.scale);
   const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
-  gi_split_kernel<SNAP><<<dim3((unsigned)slabs, (unsigned)(rows / 64)), 256, 0, st>>>(A, lda, np, ncols, rows, pl.scale,
-                                                                                       pl.data);
+  FPS_REQUIRE(slabs <= (int64_t)65535 * 65535, "gram_i8: too many slabs");
+  const unsigned gy = (unsigned)(slabs < 65535 ? slabs : 65535), gz = (unsigned)((slabs + 65534) / 65535);
+  gi_split_kernel<SNAP><<<dim3((unsigned)(rows / 64), gy, gz), 256, 0, st>>>(A, lda, np, ncols, rows, (int)slabs, pl.scale,
+                                                                              pl.data);
   count_launch(2);
   FPS_CUDA(cudaGetLastError());
   return 0;
