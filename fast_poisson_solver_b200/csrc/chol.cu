@@ -241,6 +241,15 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
   double* xb = Di + CB * (CB + 1); // [CB][SC] solved block
   const int t = threadIdx.x, warp = t / 32, lane = t % 32;
   const int c0 = blockIdx.x * SC;
+  // The sweeps are a chain of 44 dependent steps that each wait for a block of L.  Between the factorisation and
+  // this kernel the projection has streamed gigabytes through L2, so L (4 MB) would come from HBM one dependent
+  // miss at a time: pull it into L2 up front (a few CTAs' worth of prefetches; harmless when many CTAs run).
+  if (blockIdx.x < 4) {
+    const char* Lb = reinterpret_cast<const char*>(L);
+    const size_t bytes = (size_t)(CN + CB) * CN * sizeof(double);
+    for (size_t off = ((size_t)blockIdx.x * 256 + t) * 128; off < bytes; off += (size_t)min(gridDim.x, 4u) * 256 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Lb + off));
+  }
   for (int e = t; e < CN * SC; e += 256) {
     const int r = e / SC, c = e % SC;
     X[e] = (c0 + c < B) ? scale * R[(int64_t)r * ldr + c0 + c] : 0.0;
@@ -272,14 +281,17 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
     __syncthreads();
     // rows below: X[r] -= sum_m L[r][k0+m] xb[m]  (read through the mirrored upper triangle: coalesced)
     for (int r = k0 + CB + t; r < CN; r += 256) {
+      // all 32 L2 loads of the panel row in flight at once (the sweep is latency bound)
+      double l[CB];
+#pragma unroll
+      for (int m = 0; m < CB; ++m) l[m] = __ldg(L + (size_t)(k0 + m) * CN + r);
       double acc[SC];
 #pragma unroll
       for (int c = 0; c < SC; ++c) acc[c] = X[r * SC + c];
-#pragma unroll 4
-      for (int m = 0; m < CB; ++m) {
-        const double l = L[(size_t)(k0 + m) * CN + r];
 #pragma unroll
-        for (int c = 0; c < SC; ++c) acc[c] = fma(-l, xb[m * SC + c], acc[c]);
+      for (int m = 0; m < CB; ++m) {
+#pragma unroll
+        for (int c = 0; c < SC; ++c) acc[c] = fma(-l[m], xb[m * SC + c], acc[c]);
       }
 #pragma unroll
       for (int c = 0; c < SC; ++c) X[r * SC + c] = acc[c];
@@ -312,14 +324,17 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
     __syncthreads();
     // rows above: X[r] -= sum_m L[k0+m][r] xb[m]
     for (int r = t; r < k0; r += 256) {
+      // all 32 L2 loads of the panel row in flight at once (the sweep is latency bound)
+      double l[CB];
+#pragma unroll
+      for (int m = 0; m < CB; ++m) l[m] = __ldg(L + (size_t)(k0 + m) * CN + r);
       double acc[SC];
 #pragma unroll
       for (int c = 0; c < SC; ++c) acc[c] = X[r * SC + c];
-#pragma unroll 4
-      for (int m = 0; m < CB; ++m) {
-        const double l = L[(size_t)(k0 + m) * CN + r];
 #pragma unroll
-        for (int c = 0; c < SC; ++c) acc[c] = fma(-l, xb[m * SC + c], acc[c]);
+      for (int m = 0; m < CB; ++m) {
+#pragma unroll
+        for (int c = 0; c < SC; ++c) acc[c] = fma(-l[m], xb[m * SC + c], acc[c]);
       }
 #pragma unroll
       for (int c = 0; c < SC; ++c) X[r * SC + c] = acc[c];
