@@ -226,31 +226,110 @@ atb_small_kernel(const TA* __restrict__ A, int64_t lda, int M, const TB* __restr
   const int64_t kbeg = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t kend = min(n, kbeg + rows_per_cta);
   const bool has2 = t + 512 < M;
-  for (int64_t k = kbeg; k < kend; k += 4) {
-    TA a[4][3];
-    TB f[4][NB];
+  // U rows per step, every load of the step issued before the first use and no per-row predicates in the main
+  // loop: the earlier form (4 rows, bounds test per row) compiled to ~3 loads in flight per thread and streamed
+  // DH at 2.9 TB/s.
+  constexpr int U = (NB <= 2) ? 8 : 4;
+  int64_t k = kbeg;
+  for (; k + U <= kend; k += U) {
+    TA a[U][3];
+    TB f[U][NB];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool ok = k + u < kend;
+    for (int u = 0; u < U; ++u) {
       const TA* row = A + (k + u) * lda;
-      a[u][0] = ok ? __ldg(row + t) : (TA)0;
-      a[u][1] = ok ? __ldg(row + t + 256) : (TA)0;
-      a[u][2] = (ok && has2) ? __ldg(row + t + 512) : (TA)0;
+      a[u][0] = __ldg(row + t);
+      a[u][1] = __ldg(row + t + 256);
+      a[u][2] = has2 ? __ldg(row + t + 512) : (TA)0;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) f[u][j] = (ok && j < nb) ? __ldg(B + (k + u) * ldb + j) : (TB)0;
+      for (int j = 0; j < NB; ++j) f[u][j] = (j < nb) ? __ldg(B + (k + u) * ldb + j) : (TB)0;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int q = 0; q < 3; ++q)
 #pragma unroll
         for (int j = 0; j < NB; ++j) acc[q][j] = fma((double)a[u][q], (double)f[u][j], acc[q][j]);
+  }
+  for (; k < kend; ++k) {   // tail rows
+    const TA* row = A + k * lda;
+    const TA a0 = __ldg(row + t), a1 = __ldg(row + t + 256), a2 = has2 ? __ldg(row + t + 512) : (TA)0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const double fj = (j < nb) ? (double)__ldg(B + k * ldb + j) : 0.0;
+      acc[0][j] = fma((double)a0, fj, acc[0][j]);
+      acc[1][j] = fma((double)a1, fj, acc[1][j]);
+      acc[2][j] = fma((double)a2, fj, acc[2][j]);
+    }
   }
   double* out = partial + (size_t)blockIdx.x * (768 * NB);
 #pragma unroll
   for (int q = 0; q < 3; ++q)
 #pragma unroll
     for (int j = 0; j < NB; ++j) out[(t + q * 256) * NB + j] = acc[q][j];
+}
+
+// Vector form of the same kernel (lda % 4 == 0, A 16-byte aligned, M % 4 == 0): thread t owns the four columns
+// 4t..4t+3 and reads them with one 16-byte load per row (two for fp64 inputs), U rows per step.  176 of the 192
+// threads are active for M = 704.  Four times the bytes per load instruction of the scalar form.
+template <typename T>
+__device__ __forceinline__ void ldg4(const T* p, double* o);
+template <>
+__device__ __forceinline__ void ldg4<float>(const float* p, double* o) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void ldg4<double>(const double* p, double* o) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+template <int NB, typename TA, typename TB>
+__global__ void __launch_bounds__(192)
+atb_small_vec_kernel(const TA* __restrict__ A, int64_t lda, int M, const TB* __restrict__ B, int64_t ldb,
+                     int nb, int64_t n, int64_t rows_per_cta, double* __restrict__ partial) {
+  const int c0 = 4 * threadIdx.x;
+  if (c0 >= M) return;
+  double acc[4][NB];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[q][j] = 0.0;
+  const int64_t kbeg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t kend = min(n, kbeg + rows_per_cta);
+  constexpr int U = (NB <= 2) ? 8 : 4;
+  int64_t k = kbeg;
+  for (; k + U <= kend; k += U) {
+    double a[U][4];
+    double f[U][NB];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ldg4<TA>(A + (k + u) * lda + c0, a[u]);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) f[u][j] = (j < nb) ? (double)__ldg(B + (k + u) * ldb + j) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[q][j] = fma(a[u][q], f[u][j], acc[q][j]);
+  }
+  for (; k < kend; ++k) {
+    double a[4];
+    ldg4<TA>(A + k * lda + c0, a);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const double fj = (j < nb) ? (double)__ldg(B + k * ldb + j) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q][j] = fma(a[q], fj, acc[q][j]);
+    }
+  }
+  double* out = partial + (size_t)blockIdx.x * (768 * NB);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) out[(c0 + q) * NB + j] = acc[q][j];
 }
 
 template <int NB>
@@ -271,14 +350,16 @@ int launch_atb_t(const fps_ctx* ctx, const TA* A, int64_t lda, int M, const TB* 
   if (n <= 0 || M <= 0 || Nc <= 0) return 0;
   FPS_REQUIRE(M <= FP, "atb: M=%d exceeds %d", M, FP);
   if (!symmetric && Nc <= 8) {
-    int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 4, (n + 63) / 64);
+    int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 63) / 64);
     ctas = std::min<int64_t>(ctas, (int64_t)(ctx->partial_bytes / (768 * 8 * sizeof(double))));
-    const int64_t rpc = ((n + ctas - 1) / ctas + 3) / 4 * 4;
+    const int64_t rpc = ((n + ctas - 1) / ctas + 7) / 8 * 8;
     ctas = (n + rpc - 1) / rpc;
     // columns t and t+256 are always < 704 <= lda; t+512 is guarded by has2
     FPS_REQUIRE(M > 512 && lda >= M, "atb small path expects the padded feature matrix");
+    const bool vec = (lda % 4 == 0) && (M % 4 == 0) && (M <= 768) && ((uintptr_t)A % 16 == 0);
 #define FPS_SMALL(NB_)                                                                                         \
-  atb_small_kernel<NB_, TA, TB><<<(unsigned)ctas, 256, 0, st>>>(A, lda, M, B, ldb, Nc, n, rpc, ctx->partial);   \
+  if (vec) atb_small_vec_kernel<NB_, TA, TB><<<(unsigned)ctas, 192, 0, st>>>(A, lda, M, B, ldb, Nc, n, rpc, ctx->partial); \
+  else atb_small_kernel<NB_, TA, TB><<<(unsigned)ctas, 256, 0, st>>>(A, lda, M, B, ldb, Nc, n, rpc, ctx->partial);   \
   atb_small_reduce_kernel<NB_><<<(M * NB_ + 255) / 256, 256, 0, st>>>(ctx->partial, (int)ctas, M, Nc, C, ldc)
     if (Nc == 1) { FPS_SMALL(1); }
     else if (Nc == 2) { FPS_SMALL(2); }

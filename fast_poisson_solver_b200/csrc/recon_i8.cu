@@ -13,8 +13,8 @@
 // One tcgen05.mma.kind::i8 instruction multiplies one W digit (M = 256 right-hand sides per CTA pair) with the stack
 // of all four A digits of 64 points (N = 256) into the TMEM window that starts at column 64 a, so that column group
 // o collects the digit pairs with a + b = o (see gram_i8.cu).  K = 704 = 22 instructions of 32 per digit; the int32
-// accumulators cannot overflow (5 pairs x 704 x 2^14 < 2^26).  Orders 0..4 are combined in fp64 by the drain warps
-// (orders 5..7 weigh < 2^-40 of the largest term and are not read), scaled, biased and stored as fp32.
+// accumulators cannot overflow (5 pairs x 704 x 2^14 < 2^26).  Orders 0..4 are combined exactly in a 64-bit integer
+// by the drain warps (orders 5..7 weigh < 2^-40 of the largest term and are not read), scaled, biased, stored as fp32.
 // The rounding of W to 39 bits moves out by ~ sqrt(700) |w|_max 2^-39 |a|: 1e-9 of the largest term.
 #include "fps_common.cuh"
 #include "tc_ptx.cuh"
@@ -127,13 +127,13 @@ ri_split_w_kernel(const double* __restrict__ W, int64_t ldw, int B, int b_pad, c
 }
 
 // ---- the tensor-core kernel ---------------------------------------------------------------------------
-__device__ __forceinline__ void umma_i8_256(uint32_t tmem_d, uint64_t da, uint64_t db) {
+__device__ __forceinline__ void umma_i8_256(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
   constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, 1, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void ri_tmem_ld16(uint32_t taddr, int* v) {
@@ -144,15 +144,6 @@ __device__ __forceinline__ void ri_tmem_ld16(uint32_t taddr, int* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
-__device__ __forceinline__ void ri_tmem_zero16(uint32_t taddr) {
-  const int z = 0;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-      ::"r"(taddr), "r"(z)
-      : "memory");
-}
-
 struct RiParams {
   float* out;            // (n, ldo) fp32
   int64_t ldo;
@@ -236,9 +227,14 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           const int ksteps = (kb == RI_KSLABS - 1) ? (FP - 128 * (RI_KSLABS - 1)) / 32 : 4;
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t adv = (uint64_t)((j * 32) >> 4);
+            // The very first step of a tile overwrites: W digit 4 initialises columns [256, 512), digit 0 columns
+            // [0, 256); the windows of digits 1..3 then only touch initialised columns.  No zeroing pass needed.
+            const uint32_t keep = (kb > 0 || j > 0) ? 1u : 0u;
+            umma_i8_256(tmem_base + 4 * RI_TN, umma_desc<128>(sa + 4 * RI_W_BYTES) + adv, db + adv, keep);
+            umma_i8_256(tmem_base, umma_desc<128>(sa) + adv, db + adv, keep);
 #pragma unroll
-            for (int a = 0; a < RI_DW; ++a)
-              umma_i8_256(tmem_base + a * RI_TN, umma_desc<128>(sa + a * RI_W_BYTES) + adv, db + adv);
+            for (int a = 1; a < RI_DW - 1; ++a)
+              umma_i8_256(tmem_base + a * RI_TN, umma_desc<128>(sa + a * RI_W_BYTES) + adv, db + adv, 1u);
           }
           umma_commit<2>(bar_empty + 8 * stage);
           if (++stage == RI_STAGES) { stage = 0; phase ^= 1; }
@@ -251,22 +247,17 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int quad = warp % 4;          // TMEM lanes [32 quad, 32 quad + 32) = right-hand sides
     const int half = (warp - 2) / 4;    // 32 of the 64 points
     const uint32_t taddr = tmem_base + half * (RI_TN / 2) + ((uint32_t)(quad * 32) << 16);
-#pragma unroll
-    for (int o = 0; o < RI_DA + RI_DW - 1; ++o)
-#pragma unroll
-      for (int c = 0; c < RI_TN / 32; ++c) ri_tmem_zero16(taddr + o * RI_TN + c * 16);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_leader(bar_tempty);
+    if (lane == 0) mbar_arrive_leader(bar_tempty);   // the accumulators are free from the start
     uint32_t tphase = 0;
     for (int t = group; t < ntiles; t += ngroups) {
       const int jb = t % P.rhs_blocks, ib = t / P.rhs_blocks;
       const int j = jb * 2 * RI_TM + rank * RI_TM + quad * 32 + lane;
       const bool j_ok = j < P.B;
-      // out = 2^g sum_o 2^(-8 o) Acc_o,  g = g_j - 38 + 56; 2^g as a double (|g| stays far inside the exponent range)
+      // out = 2^g sum_o 2^(-8 o) Acc_o,  g = g_j - 38 + 56.  The orders 0..4 are combined exactly in a 64-bit integer
+      // S = sum_o 2^(8 (4 - o)) Acc_o  (|Acc_o| < 2^26, so |S| < 2^59), converted once: out = S 2^(g - 32) + bias.
+      // (Five int->double conversions and a fp64 Horner chain per output made the drain fp64-pipe bound.)
       const int g = j_ok ? P.gw[j] - 38 + 8 * (RI_DA + RI_DW - 2) : 0;
-      const double scale = __longlong_as_double((long long)(1023 + g) << 52);
+      const double scale = __longlong_as_double((long long)(1023 + g - 32) << 52);
       const double bj = (j_ok && P.bias) ? P.bias[j] : 0.0;
       const int64_t i0 = (int64_t)ib * RI_TN + half * (RI_TN / 2);
       mbar_wait(bar_tfull, tphase);
@@ -279,17 +270,14 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         for (int o = 0; o < RI_NORD; ++o) ri_tmem_ld16(taddr + o * RI_TN + c * 16, v[o]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int o = 0; o < RI_DA + RI_DW - 1; ++o) ri_tmem_zero16(taddr + o * RI_TN + c * 16);
-#pragma unroll
         for (int q = 0; q < 16; ++q) {
-          double s = (double)v[RI_NORD - 1][q];
+          long long S = v[0][q];
 #pragma unroll
-          for (int o = RI_NORD - 2; o >= 0; --o) s = fma(s, 0.00390625, (double)v[o][q]);
+          for (int o = 1; o < RI_NORD; ++o) S = S * 256 + v[o][q];
           const int64_t i = i0 + c * 16 + q;
-          if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)fma(s, scale, bj);
+          if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)fma((double)S, scale, bj);
         }
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_tempty);
