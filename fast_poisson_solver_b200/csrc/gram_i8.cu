@@ -21,8 +21,9 @@
 //   4. gi_reduce_kernel     G[r][c] += 2^(e_r + e_c - 12) * sum_splits sum_o 2^(-8 o) Acc_o   (fixed order, fp64)
 //
 // The same engine computes the batched RHS projection R += DH^T F (solver.py:197 + :301, launch_project_i8):
-// A = the digit planes of DH (reused from the Gram when they are still valid), B = digit planes of F (a copy on
-// the grid of each right-hand side; F itself is not modified), rectangular tiling 3 x ceil(B / 64).
+// A = the digit planes of DH (rebuilt per call: the grid only depends on the column maxima, so a DH that went
+// through the Gram is left untouched), B = digit planes of F (a copy on the grid of each right-hand side; F itself
+// is not modified), rectangular tiling 3 x ceil(B / 64).
 //
 // Every product and every partial sum is an exact integer; the only rounding is the final fp64 combination
 // (2^-53 relative), so G is the Gram of the stored A to fp64 rounding, bit-reproducible and independent of the
@@ -43,7 +44,7 @@ constexpr int GI_NACC = 7;                  // digit orders 0..6, one int32 accu
 constexpr int GI_SLAB = 128;                // points per digit-plane row chunk (split kernel granularity)
 constexpr int GI_ROWS = FPW;                // 768 feature rows per digit plane
 // K slab of the tensor-core kernel = RB points = one RB-byte swizzled row (template parameter):
-//   RB = 128: 88 KiB stages x 2;  RB = 64: 44 KiB stages x 5 (more loads in flight)
+//   RB = 128: 80 KiB stages x 2 (production);  RB = 64: 40 KiB stages x 5 (FPS_GRAM_ROWB=64, measured slower)
 constexpr int GI_RING = 220 * 1024;
 constexpr int GI_SMEM = GI_RING + 1024 + 256;
 constexpr int GI_THREADS = 320;             // TMA warp, MMA warp, 8 drain warps
