@@ -111,6 +111,7 @@ struct TcParams {
   int64_t ld;
   int64_t rows;   // valid activation rows = points * S
   int nk;         // K slabs of TK
+  int tail_steps; // 32-byte MMA steps of the last slab that hold real K (the rest is TMA zero fill: skipped)
   int row_tiles;  // ceil(rows / 256)
   int stats;      // FPS_TC_STATS=1: cycle accounting of CTA 0 into g_tc_stats
   int seg;        // K slabs per tensor-core accumulation segment
@@ -289,8 +290,10 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
             const uint64_t a_hi = umma_desc<ROW_BYTES>(sa), a_lo = umma_desc<ROW_BYTES>(sa + BOX_BYTES);
             const uint64_t b_hi = umma_desc<ROW_BYTES>(sa + 2 * BOX_BYTES),
                            b_lo = umma_desc<ROW_BYTES>(sa + (2 + B_BOXES) * BOX_BYTES);
+            const int jn = (kc == P.nk - 1) ? P.tail_steps : ROW_BYTES / 32;
 #pragma unroll
             for (int j = 0; j < ROW_BYTES / 32; ++j) {
+              if (j >= jn) break;
               const uint64_t adv = (uint64_t)((j * 32) >> 4);  // +32 bytes of K per MMA inside the swizzle row
               const uint32_t first = (kc > kc0 || j > 0) ? 1u : 0u;
               if (F16) {
@@ -568,6 +571,11 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   const bool wide = f16 && s->pair && s->rb == 128;     // 128-byte slab rows (SWIZZLE_128B)
   const int slab_k = (wide ? 128 : 64) / (f16 ? 2 : 4);   // K elements per slab
   P.nk = (L.Kp + slab_k - 1) / slab_k;                    // an overhanging last slab is zero-filled by TMA
+  {
+    const int step_k = f16 ? 16 : 8;                      // K elements per MMA instruction
+    const int rem = L.Kp - (P.nk - 1) * slab_k;           // real K in the last slab
+    P.tail_steps = (rem + step_k - 1) / step_k;
+  }
   for (int i = 0; i < 4; ++i) {
     P.in_inv[i] = f16 ? 1.0f / (W16_SCALE * ctx->act_scale[l].s[i]) : 1.0f;
     P.out_sc[i] = ctx->act_scale[l + 1 < NLAYER ? l + 1 : l].s[i];
