@@ -25,6 +25,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.fps_version() == 100
 
 
+def test_ctypes_prototypes_match_header_arity():
+    """Every prototype of include/fps_sm100.h and its ctypes twin in _lib.SIGNATURES take the same number of arguments."""
+    from fast_poisson_solver_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "fps_sm100.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\b(fps_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header))
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert name in protos, name
+        args = protos[name].strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(argtypes), (name, n, len(argtypes))
+
+
+def test_library_contains_blackwell_tensor_and_tma_instructions():
+    """SASS evidence without a GPU: tcgen05 MMAs in fp16 (features) and int8 (exact Gram / projection /
+    reconstruction), TMEM loads/stores and TMA loads are in the shipped library; no legacy HMMA path."""
+    import subprocess
+    from fast_poisson_solver_b200 import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTCIMMA", "LDTM", "STTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+    assert "DMMA" in sass          # fp64 tensor path of the small / float64-mode kernels
+
+
 def test_library_is_sm100a_only():
     import subprocess
     from fast_poisson_solver_b200 import _lib
