@@ -18,9 +18,15 @@ Deliberate deviations from the reference:
   * ``solve`` also accepts ``f`` of shape (N, B) with ``bc`` of shape (N_bc, B) (or (B,) constants)
     and returns (N+N_bc, B) / (N, B) / (N_bc, B) tensors - the reference is single-RHS only.
   * ``runtime`` is measured with a stream synchronise on both sides.
-  * precision=torch.float32: features are evaluated at fp32 grade (3xTF32 tensor-core contractions,
-    fp64 Fourier phases); Gram matrix, RHS projection, factorisation and reconstruction accumulate in
-    fp64.  precision=torch.float64: everything, including the feature network, runs in fp64 (DMMA).
+  * precision=torch.float32: features are evaluated at fp32 grade (tensor-core contractions on fp16 hi/lo
+    operand planes, three MMAs per product; fp64 Fourier phases); Gram matrix, RHS projection and
+    reconstruction are fp64 grade - exact integer arithmetic on the int8 tensor cores for N >= 16384 points
+    (and >= 32 right-hand sides), fp64 accumulation otherwise - and the factorisation is fp64.
+    precision=torch.float64: everything, including the feature network, runs in fp64 (DMMA).
+  * For N >= 16384 the stored ``DH`` (and ``H`` once a batched solve has used it) is snapped to a 31-bit
+    fixed-point grid per feature column: elements below 2^-7 of the column maximum move by less than 2^-31 of
+    it (under 1 % of one fp32 ulp of the maximum), all others are unchanged.  The Gram matrix is then the exact
+    Gram of the stored ``DH`` (csrc/gram_i8.cu).
   * ``distributed=True``: every rank passes ITS shard of the collocation / boundary points and of
     the rows of ``f``; one all-reduce of the packed [Gram | BC Gram | column sums | counts] buffer
     in precompute and one of the projected right-hand sides per solve.
