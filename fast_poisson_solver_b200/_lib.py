@@ -19,6 +19,7 @@ NFREQ = 200
 NHIDDEN = 5
 ENGINE_SIMT = 0
 ENGINE_TCGEN05 = 1
+XOP_BYTES = 16384  # FPS_XOP_BYTES
 
 _f32p = C.POINTER(C.c_float)
 
@@ -46,15 +47,29 @@ SIGNATURES = {
     "fps_get_engine": (_i32, [_vp]),
     "fps_calibrate_scales": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "fps_get_scales": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "fps_set_scales": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "fps_get_calibration": (_i32, [_vp, C.POINTER(_f64)]),
     "fps_workspace_bytes": (C.c_size_t, [_vp]),
     "fps_features": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "fps_gram_accum": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fps_colsum_accum": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fps_assemble_factor": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(_f64), C.POINTER(_f64), _i32, _vp, _vp, _vp]),
+    "fps_assemble_factor_packed": (_i32, [_vp, _vp, C.POINTER(_f64), C.POINTER(_f64), _i32, _vp, _vp, _vp]),
     "fps_project_rhs": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "fps_solve_factored": (_i32, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "fps_reconstruct": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "fps_mse": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "fps_sse_columns": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
+    "fps_sse_columns_f64": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
+    "fps_exact_min_rows": (_i64, []),
+    "fps_gram_planes_bytes": (C.c_size_t, [_i64]),
+    "fps_recon_planes_bytes": (C.c_size_t, [_i64]),
+    "fps_reserve_workspace": (_i32, [_vp, _i64, _i32]),
+    "fps_features_x": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
+    "fps_gram_accum_x": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "fps_project_rhs_x": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "fps_recon_planes_build": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),
+    "fps_reconstruct_x": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "fps_features_f64": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "fps_gram_accum_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "fps_colsum_accum_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
@@ -62,6 +77,12 @@ SIGNATURES = {
     "fps_reconstruct_f64": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "fps_sine_sources": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
     "fps_sine_sources_f64": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "fps_perlin_sources": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "fps_perlin_sources_f64": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "fps_grid_points": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "fps_fd_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32]),
+    "fps_fd_solve": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, C.c_size_t, _vp]),
+    "fps_fd_solve_f32": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, C.c_size_t, _vp]),
     "fps_launch_count": (_i64, []),
     "fps_profile_enable": (_i32, [_vp, _i32]),
     "fps_profile_reset": (_i32, [_vp]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfps_sm100.so")
-SOURCES = ["fps_api.cu", "fourier.cu", "layer_simt.cu", "layer_tc.cu", "features_f64.cu", "gemm_f64.cu", "gram_i8.cu", "recon_i8.cu", "chol.cu", "sources.cu"]
+SOURCES = ["fps_api.cu", "fourier.cu", "layer_simt.cu", "layer_tc.cu", "features_f64.cu", "gemm_f64.cu", "gram_i8.cu", "recon_i8.cu", "xop.cu", "chol.cu", "sources.cu", "fd_dst.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -15,6 +15,7 @@
 // when the factorisation reports a pivot <= eps*max_diag through `info`.
 #include "fps_common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace fps {
 
@@ -23,10 +24,15 @@ constexpr int CB = 32;   // panel width
 constexpr int CNB = CN / CB;  // 22 panels
 
 // ---- assemble ----------------------------------------------------------------------------------
+// counts != null: {N, N_bc} are read from device memory (the all-reduced packed buffer) and lam_over_n holds lambda
 __global__ void assemble_kernel(const double* __restrict__ G, const double* __restrict__ Gbc,
                                 const double* __restrict__ s, double lam_over_n, double inv_nbc, double jitter,
-                                double* __restrict__ L) {
+                                const double* __restrict__ counts, double* __restrict__ L) {
   const int i = blockIdx.x;
+  if (counts) {
+    lam_over_n = lam_over_n / counts[0];
+    inv_nbc = 1.0 / counts[1];
+  }
   for (int j = threadIdx.x; j < CN; j += blockDim.x) {
     double v;
     if (i < F && j < F) {
@@ -194,19 +200,236 @@ __global__ void chol_dinv_kernel(double* __restrict__ L) {
   for (int i = 0; i < CB; ++i) L[(size_t)(CN + i) * CN + k0 + j] = x[i];
 }
 
+// ---- the whole factorisation in ONE launch -------------------------------------------------------------------------
+// assemble -> max diagonal -> 22 x (panel, trailing update) -> fixup + diagonal-block inverses, with a grid-wide barrier
+// between the phases instead of 48 kernel launches (the 704 x 704 problem is 0.11 GFLOP: pure latency).  CF_CTAS CTAs,
+// one per SM and all co-resident (the barrier spins): 66 = the tile count of the first trailing update.  Data that
+// crosses CTAs goes through L2 (__ldcg / __stcg); the barrier is a monotone counter in global memory (zeroed by the
+// host before the launch), bounded spin + trap like the mbarrier waits of the tensor-core kernels.
+constexpr int CF_CTAS = 66;
+
+__device__ __forceinline__ void cf_grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
+      if (++spins > 400000000u) {
+        printf("fps chol_fused: grid barrier timeout (block %d target %u)\n", blockIdx.x, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1)
+chol_fused_kernel(const double* __restrict__ G, const double* __restrict__ Gbc, const double* __restrict__ sv,
+                  double lam, double n_total, double nbc_total, const double* __restrict__ counts, double jitter,
+                  double* __restrict__ L, double* __restrict__ Dfac, unsigned long long* __restrict__ dmax_bits,
+                  unsigned* __restrict__ bar, int* __restrict__ info) {
+  __shared__ double D[CB][CB + 1];
+  __shared__ double Pi[64][CB + 1];
+  __shared__ double Pj[64][CB + 1];
+  __shared__ double red[8];
+  const int t = threadIdx.x;
+  unsigned target = 0;
+  if (counts) { n_total = counts[0]; nbc_total = counts[1]; }
+  const double lam_over_n = lam / n_total, inv_nbc = 1.0 / nbc_total;
+
+  // ---- assemble (solver.py:195-196 with the centering matrix folded in) + max diagonal
+  double m = 0.0;
+  for (int i = blockIdx.x; i < CN; i += gridDim.x) {
+    for (int j = t; j < CN; j += 256) {
+      double v;
+      if (i < F && j < F) {
+        v = lam_over_n * G[(size_t)i * CN + j] + (Gbc[(size_t)i * CN + j] - sv[i] * sv[j] * inv_nbc) * inv_nbc;
+        if (i == j) { v += jitter; m = fmax(m, v); }
+      } else {
+        v = (i == j) ? 1.0 : 0.0;
+      }
+      __stcg(L + (size_t)i * CN + j, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (t % 32 == 0) red[t / 32] = m;
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+    atomicMax(dmax_bits, (unsigned long long)__double_as_longlong(m));   // m >= 0: the bit patterns order like the values
+    if (blockIdx.x == 0) *info = 0;
+  }
+  cf_grid_barrier(bar, target);
+  const double dmax = __longlong_as_double((long long)__ldcg(dmax_bits));
+  const double tol = DBL_EPSILON * dmax;
+  const double safe = dmax > 0.0 ? dmax : 1.0;
+
+  for (int kb = 0; kb < CNB; ++kb) {
+    const int k0 = kb * CB;
+    const int below = CN - (k0 + CB);
+    // ---- panel: CTAs that own rows below (256 per CTA) factor the diagonal block redundantly, then solve their rows
+    const int my_r = k0 + CB + blockIdx.x * 256 + t;
+    const bool cta_has_rows = blockIdx.x * 256 < below || blockIdx.x == 0;
+    if (cta_has_rows) {
+      for (int e = t; e < CB * CB; e += 256) D[e / CB][e % CB] = __ldcg(L + (size_t)(k0 + e / CB) * CN + k0 + e % CB);
+      for (int j = 0; j < CB; ++j) {
+        __syncthreads();
+        double d = D[j][j];
+        const bool bad = !(d > tol);
+        if (bad) d = safe;  // keep the arithmetic finite; the host sees info != 0 and retries with a shift
+        const double ljj = sqrt(d);
+        __syncthreads();
+        if (t < CB) {
+          if (t == j) {
+            D[j][j] = ljj;
+            if (bad && blockIdx.x == 0) atomicCAS(info, 0, k0 + j + 1);
+          } else if (t > j) {
+            D[t][j] = D[t][j] / ljj;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = t + 256 * q;
+          const int i = e / CB, mm = e % CB;
+          if (mm > j && i >= mm) D[i][mm] -= D[i][j] * D[mm][j];
+        }
+      }
+      __syncthreads();
+      if (blockIdx.x == 0)
+        for (int e = t; e < CB * CB; e += 256) Dfac[(size_t)kb * CB * CB + e] = (e % CB <= e / CB) ? D[e / CB][e % CB] : 0.0;
+      if (my_r < CN) {
+        double x[CB];
+        double* row = L + (size_t)my_r * CN + k0;
+#pragma unroll
+        for (int j = 0; j < CB; ++j) x[j] = __ldcg(row + j);
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          double sacc = x[j];
+#pragma unroll
+          for (int mm = 0; mm < j; ++mm) sacc = fma(-x[mm], D[j][mm], sacc);
+          x[j] = sacc / D[j][j];
+        }
+#pragma unroll
+        for (int j = 0; j < CB; ++j) __stcg(row + j, x[j]);
+      }
+    }
+    if (below <= 0) break;
+    cf_grid_barrier(bar, target);
+    // ---- trailing update A22 -= L21 L21^T on lower-triangular 64 x 64 tiles
+    const int base = k0 + CB;
+    const int t64 = (below + 63) / 64;
+    const int ntile = t64 * (t64 + 1) / 2;
+    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+      int ti = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+      while (ti * (ti + 1) / 2 > tile) --ti;
+      const int tj = tile - ti * (ti + 1) / 2;
+      const int i0 = base + ti * 64, j0 = base + tj * 64;
+      __syncthreads();
+      for (int e = t; e < 64 * CB; e += 256) {
+        const int r = e / CB, c = e % CB;
+        Pi[r][c] = (i0 + r < CN) ? __ldcg(L + (size_t)(i0 + r) * CN + k0 + c) : 0.0;
+        Pj[r][c] = (j0 + r < CN) ? __ldcg(L + (size_t)(j0 + r) * CN + k0 + c) : 0.0;
+      }
+      __syncthreads();
+      const int tx = t % 16, ty = t / 16;
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CB; ++k) {
+        double pa[4], pb[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) pa[a] = Pi[ty + 16 * a][k];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pb[b] = Pj[tx + 16 * b][k];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(pa[a], pb[b], acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+          if (i < CN && j <= i) {
+            double* q = L + (size_t)i * CN + j;
+            __stcg(q, __ldcg(q) - acc[a][b]);
+          }
+        }
+    }
+    cf_grid_barrier(bar, target);
+  }
+  cf_grid_barrier(bar, target);
+  // ---- fixup: install the factored diagonal blocks, mirror L into the upper triangle
+  for (int i = blockIdx.x; i < CN; i += gridDim.x) {
+    const int kb = i / CB;
+    for (int j = t; j <= i; j += 256) {
+      double v;
+      if (j >= kb * CB) v = __ldcg(Dfac + (size_t)kb * CB * CB + (i - kb * CB) * CB + (j - kb * CB));
+      else v = __ldcg(L + (size_t)i * CN + j);
+      __stcg(L + (size_t)i * CN + j, v);
+      if (j < i) __stcg(L + (size_t)j * CN + i, v);
+    }
+  }
+  // ---- inverses of the diagonal blocks (rows 704..735 of the factor buffer), one warp per block, from Dfac
+  for (int kb = blockIdx.x; kb < CNB; kb += gridDim.x) {
+    __syncthreads();
+    for (int e = t; e < CB * CB; e += 256) D[e / CB][e % CB] = __ldcg(Dfac + (size_t)kb * CB * CB + e);
+    __syncthreads();
+    if (t < CB) {
+      const int j = t;
+      double x[CB];
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        double sacc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int mm = 0; mm < i; ++mm) sacc = fma(-D[i][mm], x[mm], sacc);
+        x[i] = (i >= j) ? sacc / D[i][i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < CB; ++i) L[(size_t)(CN + i) * CN + kb * CB + j] = x[i];
+    }
+  }
+}
+
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
-                           int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,
-                           cudaStream_t st) {
-  FPS_REQUIRE(n_total > 0 && nbc_total > 0, "assemble: empty problem (N=%lld, N_bc=%lld)", (long long)n_total,
+                           int64_t nbc_total, const double* d_counts, const double* h_lambdas, const double* h_jitter,
+                           int n_lambda, double* L, int* info, cudaStream_t st) {
+  FPS_REQUIRE(d_counts || (n_total > 0 && nbc_total > 0), "assemble: empty problem (N=%lld, N_bc=%lld)", (long long)n_total,
               (long long)nbc_total);
   // scratch in the partial workspace: [0] = max diag, then the 22 factored diagonal blocks
   double* scal = ctx->partial;
   double* Dfac = ctx->partial + 8;
+  static const int fused_env = getenv("FPS_CHOL_FUSED") ? atoi(getenv("FPS_CHOL_FUSED")) : 1;
+  if (fused_env && ctx->sm_count >= CF_CTAS) {
+    for (int li = 0; li < n_lambda; ++li) {
+      double* Ll = L + (size_t)li * FPS_LROWS * CN;
+      // scal[0] = max diagonal (as ordered bits), scal[1] = barrier counter
+      FPS_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(double), st));
+      chol_fused_kernel<<<CF_CTAS, 256, 0, st>>>(G, Gbc, s, h_lambdas[li], (double)n_total, (double)nbc_total, d_counts,
+                                                 h_jitter ? h_jitter[li] : 0.0, Ll, Dfac,
+                                                 reinterpret_cast<unsigned long long*>(scal),
+                                                 reinterpret_cast<unsigned*>(scal + 1), info + li);
+    }
+    count_launch(n_lambda);
+    FPS_CUDA(cudaGetLastError());
+    return 0;
+  }
   for (int li = 0; li < n_lambda; ++li) {
     double* Ll = L + (size_t)li * FPS_LROWS * CN;
     const double lam = h_lambdas[li];
     const double jitter = h_jitter ? h_jitter[li] : 0.0;
-    assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam / (double)n_total, 1.0 / (double)nbc_total, jitter, Ll);
+    if (d_counts) assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam, 0.0, jitter, d_counts, Ll);
+    else assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam / (double)n_total, 1.0 / (double)nbc_total, jitter, nullptr, Ll);
     diagmax_kernel<<<1, 256, 0, st>>>(Ll, scal, info + li);
     for (int kb = 0; kb < CNB; ++kb) {
       const int below = CN - (kb + 1) * CB;
@@ -355,15 +578,19 @@ solve_factored_kernel(const double* __restrict__ L, const double* __restrict__ R
   }
 }
 
+constexpr size_t SOLVE_SMEM = (size_t)(CN * SC + 2 * CB * (CB + 1) + CB * SC) * sizeof(double);
+
+// per context (= per device): the function attribute is a per-device setting
+int chol_init(fps_ctx* ctx) {
+  (void)ctx;
+  FPS_CUDA(cudaFuncSetAttribute(solve_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+  return 0;
+}
+
 int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
                           const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st) {
   if (B <= 0) return 0;
-  const size_t smem = (size_t)(CN * SC + 2 * CB * (CB + 1) + CB * SC) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FPS_CUDA(cudaFuncSetAttribute(solve_factored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = SOLVE_SMEM;
   solve_factored_kernel<<<(B + SC - 1) / SC, 256, smem, st>>>(L, R, ldr, B, scale, s, sum_bc, 1.0 / (double)nbc_total,
                                                               W, bias);
   count_launch();

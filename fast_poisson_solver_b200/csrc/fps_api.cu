@@ -195,17 +195,22 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   }
   ctx->partial_bytes = (size_t)1024 * 64 * 64 * sizeof(double);  // 32 MiB of split-K tiles
   FPS_CUDA(cudaMalloc(&ctx->partial, ctx->partial_bytes));
-  FPS_CUDA(cudaMalloc(&ctx->dh_cmax, FPW * sizeof(unsigned)));
+  FPS_CUDA(cudaMalloc(&ctx->xop_tmp, 2 * sizeof(Xop)));
+  FPS_CUDA(cudaMemset(ctx->xop_tmp, 0, 2 * sizeof(Xop)));
+  FPS_CUDA(cudaMalloc(&ctx->dh_cal_cmax, FPW * sizeof(unsigned)));
+  FPS_CUDA(cudaMemset(ctx->dh_cal_cmax, 0, FPW * sizeof(unsigned)));
   FPS_CUDA(cudaMalloc(&ctx->tc_sched, 2 * sizeof(int)));
   FPS_CUDA(cudaMemset(ctx->tc_sched, 0, 2 * sizeof(int)));
   ctx->workspace_bytes = 4 * plane + ctx->partial_bytes;
-  if (tc_init(ctx)) { fps_destroy(ctx); return 3; }
+  if (tc_init(ctx) || chol_init(ctx)) { fps_destroy(ctx); return 3; }
   *out = ctx;
   return 0;
 }
 
 int fps_destroy(fps_ctx* ctx) {
   if (!ctx) return 0;
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);   // the caller's current device is restored below (torch relies on it)
   cudaSetDevice(ctx->device);
   tc_destroy(ctx);
   gram_i8_destroy(ctx);
@@ -224,40 +229,81 @@ int fps_destroy(fps_ctx* ctx) {
     cudaFree(ctx->act[i].hi);
   }
   cudaFree(ctx->partial);
-  cudaFree(ctx->dh_cmax);
+  cudaFree(ctx->xop_tmp);
+  cudaFree(ctx->dh_cal_cmax);
   cudaFree(ctx->tc_sched);
   delete ctx->prof;
   delete ctx;
+  if (prev_device >= 0) cudaSetDevice(prev_device);
   return 0;
 }
 
-// ---- operand-scale calibration for the FP16x2-split planes ----------------------------------------
+// ---- calibration on a sample of the caller's points ----------------------------------------------------------
+// relative L2 distance of two (rows x FP) matrices -> out[0] = sum (a-b)^2, out[1] = sum b^2 (fp64 atomics: diagnostic)
+__global__ void rel_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count,
+                                double* __restrict__ out) {
+  double d2 = 0.0, b2 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = a[i], y = b[i];
+    d2 += (x - y) * (x - y);
+    b2 += y * y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+  }
+  if (threadIdx.x % 32 == 0) {
+    atomicAdd(out, d2);
+    atomicAdd(out + 1, b2);
+  }
+}
+
+// run the first `np` sample points through all six layers of `engine` in the given operand format; H / DH out
+static int cal_forward(fps_ctx* ctx, const double* x, const double* y, int64_t np, int engine, int f16, float* H, float* DH,
+                       unsigned* d_max, cudaStream_t st) {
+  const int f16_saved = ctx->f16;
+  ctx->f16 = f16;
+  for (int i = 0; i < 2; ++i) ctx->act[i].f16 = f16;
+  int cur = 0, rc = launch_fourier(ctx, x, y, np, NSTREAM, ctx->act[cur], st);
+  for (int l = 0; l < NLAYER && rc == 0; ++l) {
+    const bool last = l == NLAYER - 1;
+    if (d_max) {
+      plane_absmax_kernel<4><<<512, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, ctx->layer[l].Kp,
+                                                  d_max + 4 * l);
+      count_launch();
+    }
+    rc = (engine == FPS_ENGINE_TCGEN05)
+             ? launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, last, H, DH, FP, nullptr, st)
+             : launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, last, H, DH, FP, st);
+    cur ^= 1;
+  }
+  ctx->f16 = f16_saved;
+  for (int i = 0; i < 2; ++i) ctx->act[i].f16 = f16_saved;
+  return rc;
+}
+
+// 1. operand scales of the FP16x2-split planes: the sample runs through the scale-free TF32-format planes and every
+//    layer input is measured;
+// 2. max |DH| per feature over the sample -> the calibrated fixed-point grid of the fused last-layer epilogue
+//    (fps_features_x; an element beyond it raises a flag and the split is redone from the true maxima);
+// 3. once per context: the production tensor-core path (fp16 planes, accumulator-gain compensation, layer_tc.cu
+//    kappa_of) is checked against the fp32 FFMA engine on the sample; if the compensated result is further away than
+//    the uncompensated one the gain is switched off for this weight set.
 int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t n, void* stream) {
   FPS_REQUIRE(ctx && x && y && n > 0, "fps_calibrate_scales: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t np = n < 512 ? n : 512;
-  unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->partial);  // NLAYER x 4 words of scratch
+  // scratch in the split-K workspace: [0, 4 KiB) maxima | H | DH | H2 | DH2 (512 x 704 floats each) | 4 doubles
+  unsigned int* d_max = reinterpret_cast<unsigned int*>(ctx->partial);
+  float* Hs = reinterpret_cast<float*>(ctx->partial) + 1024;
+  float* DHs = Hs + 512 * FP;
+  float* H2 = DHs + 512 * FP;
+  float* DH2 = H2 + 512 * FP;
+  double* d_err = reinterpret_cast<double*>(DH2 + 512 * FP);
   FPS_CUDA(cudaMemsetAsync(d_max, 0, NLAYER * 4 * sizeof(unsigned int), st));
-  // run the sample through the scale-free TF32-format planes (3xTF32 tensor-core kernel, or the fp32 cross-check
-  // engine when that is the selected one) and look at every layer input
-  const int f16_saved = ctx->f16;
-  ctx->f16 = 0;
-  for (int i = 0; i < 2; ++i) ctx->act[i].f16 = 0;
-  int cur = 0, rc = launch_fourier(ctx, x, y, np, NSTREAM, ctx->act[cur], st);
-  for (int l = 0; l < NLAYER && rc == 0; ++l) {
-    const int K = ctx->layer[l].Kp;
-    plane_absmax_kernel<4><<<512, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, K, d_max + 4 * l);
-    count_launch();
-    if (l < NLAYER - 1) {
-      rc = (ctx->engine == FPS_ENGINE_TCGEN05)
-               ? launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st)
-               : launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, NSTREAM, false, nullptr, nullptr, FP, st);
-      cur ^= 1;
-    }
-  }
-  ctx->f16 = f16_saved;
-  for (int i = 0; i < 2; ++i) ctx->act[i].f16 = f16_saved;
-  if (rc) return rc;
+  if (int rc = cal_forward(ctx, x, y, np, ctx->engine, 0, Hs, DHs, d_max, st)) return rc;
+  if (int rc = xop_colmax(ctx, DHs, FP, np, FP, ctx->dh_cal_cmax, st)) return rc;
   unsigned int h_max[NLAYER * 4];
   FPS_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
   FPS_CUDA(cudaStreamSynchronize(st));
@@ -274,6 +320,36 @@ int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t
       if (sc < 1.0e-6f) sc = 1.0e-6f;
       ctx->act_scale[l].s[s] = sc;
     }
+  ctx->dh_cal_valid = 1;
+  if (ctx->engine == FPS_ENGINE_TCGEN05 && ctx->f16 && !ctx->gain_checked) {
+    // reference: the fp32 FFMA engine on the same sample (round-to-nearest accumulation, no compensation needed)
+    if (int rc = cal_forward(ctx, x, y, np, FPS_ENGINE_SIMT, 1, H2, DH2, nullptr, st)) return rc;
+    double h_err[2][4];
+    for (int pass = 0; pass < 2; ++pass) {
+      ctx->gain_off = pass;
+      FPS_CUDA(cudaMemsetAsync(d_err, 0, 4 * sizeof(double), st));
+      if (int rc = cal_forward(ctx, x, y, np, FPS_ENGINE_TCGEN05, 1, Hs, DHs, nullptr, st)) return rc;
+      rel_diff_kernel<<<64, 256, 0, st>>>(Hs, H2, np * FP, d_err);
+      rel_diff_kernel<<<64, 256, 0, st>>>(DHs, DH2, np * FP, d_err + 2);
+      count_launch(2);
+      FPS_CUDA(cudaMemcpyAsync(h_err[pass], d_err, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      FPS_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      ctx->cal_err[2 * pass] = h_err[pass][1] > 0 ? sqrt(h_err[pass][0] / h_err[pass][1]) : 0.0;
+      ctx->cal_err[2 * pass + 1] = h_err[pass][3] > 0 ? sqrt(h_err[pass][2] / h_err[pass][3]) : 0.0;
+    }
+    // keep the compensation unless the uncompensated kernel is clearly closer to the fp32 engine on DH
+    ctx->gain_off = (ctx->cal_err[3] < 0.8 * ctx->cal_err[1]) ? 1 : 0;
+    ctx->gain_checked = 1;
+  }
+  return 0;
+}
+
+int fps_get_calibration(const fps_ctx* ctx, double* h_out5) {
+  FPS_REQUIRE(ctx && h_out5, "fps_get_calibration: null argument");
+  for (int i = 0; i < 4; ++i) h_out5[i] = ctx->cal_err[i];
+  h_out5[4] = ctx->gain_checked ? (ctx->gain_off ? 0.0 : 1.0) : -1.0;
   return 0;
 }
 
@@ -281,6 +357,16 @@ int fps_get_scales(const fps_ctx* ctx, float* out24) {
   FPS_REQUIRE(ctx && out24, "fps_get_scales: null argument");
   for (int l = 0; l < NLAYER; ++l)
     for (int s = 0; s < 4; ++s) out24[4 * l + s] = ctx->act_scale[l].s[s];
+  return 0;
+}
+
+int fps_set_scales(fps_ctx* ctx, const float* in24) {
+  FPS_REQUIRE(ctx && in24, "fps_set_scales: null argument");
+  for (int l = 0; l < NLAYER; ++l)
+    for (int s = 0; s < 4; ++s) {
+      FPS_REQUIRE(in24[4 * l + s] > 0.f && in24[4 * l + s] < 1.0e30f, "fps_set_scales: scale %d is not positive", 4 * l + s);
+      ctx->act_scale[l].s[s] = in24[4 * l + s];
+    }
   return 0;
 }
 
@@ -293,24 +379,15 @@ int fps_set_engine(fps_ctx* ctx, int engine) {
 int fps_get_engine(const fps_ctx* ctx) { return ctx ? ctx->engine : -1; }
 size_t fps_workspace_bytes(const fps_ctx* ctx) { return ctx ? ctx->workspace_bytes : 0; }
 
-int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, float* H, float* DH, int64_t ld,
-                 void* stream) {
-  FPS_REQUIRE(ctx && x && y && H, "fps_features: null argument");
-  FPS_REQUIRE(ld >= FP && ld % 4 == 0, "fps_features: ld=%lld must be >= %d and a multiple of 4", (long long)ld, FP);
-  FPS_REQUIRE((uintptr_t)H % 16 == 0 && (uintptr_t)DH % 16 == 0, "fps_features: H/DH must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+// the per-wave layer pipeline shared by fps_features and fps_features_x
+static int features_run(fps_ctx* ctx, const double* x, const double* y, int64_t n, float* H, float* DH, int64_t ld,
+                        Xop* xdh, int8_t* gplanes, int snap_h, cudaStream_t st) {
   const int streams = DH ? NSTREAM : 1;
   // value-only evaluation carries one stream, so four times as many points fit a workspace wave
   const int64_t wave = (int64_t)ctx->chunk * (NSTREAM / streams);
-  if (DH) {
-    // the tensor-core engine's last layer records max |DH| per feature for fps_gram_accum's int8 path
-    ctx->dh_cmax_of = nullptr;
-    if (ctx->engine == FPS_ENGINE_TCGEN05) {
-      FPS_CUDA(cudaMemsetAsync(ctx->dh_cmax, 0, FPW * sizeof(unsigned), st));
-      ctx->dh_cmax_of = DH;
-      ctx->dh_cmax_n = n;
-    }
-  }
+  // the dynamic tile scheduler's counters return to zero at the end of every launch; clear them anyway so that an
+  // aborted launch (device fault, timeout) cannot make later calls skip tiles
+  if (ctx->engine == FPS_ENGINE_TCGEN05) FPS_CUDA(cudaMemsetAsync(ctx->tc_sched, 0, 2 * sizeof(int), st));
   for (int64_t p0 = 0; p0 < n; p0 += wave) {
     const int64_t np = (n - p0 < wave) ? n - p0 : wave;
     int cur = 0;
@@ -324,10 +401,13 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
       float* DHc = DH ? DH + p0 * ld : nullptr;
       int rc;
       ProfScope ps(ctx, l == 0 ? FPS_PROF_LAYER0 : (last ? FPS_PROF_LAST : FPS_PROF_HIDDEN), st);
-      if (ctx->engine == FPS_ENGINE_TCGEN05)
-        rc = launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, streams, last, Hc, DHc, ld, st);
-      else
+      if (ctx->engine == FPS_ENGINE_TCGEN05) {
+        const FusedOut fo{xdh, gplanes, p0, snap_h};
+        rc = launch_layer_tc(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, streams, last, Hc, DHc, ld,
+                             (last && DH && (xdh || snap_h)) ? &fo : nullptr, st);
+      } else {
         rc = launch_layer_simt(ctx, l, ctx->act[cur], ctx->act[cur ^ 1], np, streams, last, Hc, DHc, ld, st);
+      }
       if (rc) return rc;
       cur ^= 1;
     }
@@ -335,13 +415,65 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, floa
   return 0;
 }
 
+int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n, float* H, float* DH, int64_t ld,
+                 void* stream) {
+  FPS_REQUIRE(ctx && x && y && H, "fps_features: null argument");
+  FPS_REQUIRE(ld >= FP && ld % 4 == 0, "fps_features: ld=%lld must be >= %d and a multiple of 4", (long long)ld, FP);
+  FPS_REQUIRE((uintptr_t)H % 16 == 0 && (uintptr_t)DH % 16 == 0, "fps_features: H/DH must be 16-byte aligned");
+  return features_run(ctx, x, y, n, H, DH, ld, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+// FPS_FUSE=0 keeps the digit split out of the feature kernel (A/B comparisons, tests of the unfused path)
+static bool fuse_enabled() {
+  static const int v = getenv("FPS_FUSE") ? atoi(getenv("FPS_FUSE")) : 1;
+  return v != 0;
+}
+
+int fps_features_x(fps_ctx* ctx, const double* x, const double* y, int64_t n, float* H, float* DH, int64_t ld,
+                   void* xop_h, void* xop_dh, void* gram_planes, int* h_planes_written, void* stream) {
+  FPS_REQUIRE(ctx && x && y && H && DH && xop_h && xop_dh, "fps_features_x: null argument");
+  FPS_REQUIRE(ld >= FP && ld % 4 == 0, "fps_features_x: ld=%lld must be >= %d and a multiple of 4", (long long)ld, FP);
+  FPS_REQUIRE((uintptr_t)H % 16 == 0 && (uintptr_t)DH % 16 == 0 && (uintptr_t)gram_planes % 16 == 0 &&
+                  (uintptr_t)xop_h % 16 == 0 && (uintptr_t)xop_dh % 16 == 0,
+              "fps_features_x: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Xop* xh = static_cast<Xop*>(xop_h);
+  Xop* xdh = static_cast<Xop*>(xop_dh);
+  if (h_planes_written) *h_planes_written = 0;
+  // H = tanh(.) lies in [-1, 1]: the uniform 2^-30 grid needs no maxima and cannot overflow
+  if (int rc = xop_uniform(xh, 0, st)) return rc;
+  FPS_CUDA(cudaMemsetAsync(xdh, 0, sizeof(Xop), st));
+  const bool tc = ctx->engine == FPS_ENGINE_TCGEN05;
+  const bool fused = tc && fuse_enabled() && gram_planes && ctx->dh_cal_valid && n > 0;
+  if (fused) {
+    // calibrated grid of DH: two bits above the sample maxima (fps_calibrate_scales)
+    if (int rc = xop_exps(ctx->dh_cal_cmax, FP, XOP_ROWS, 2, xdh->exps, xdh->scale, nullptr, st)) return rc;
+    // the feature kernel covers whole 64-point tiles; the rest of the last 128-point slab must read as zero digits
+    const int64_t slabs = (n + 127) / 128;
+    const size_t slab_bytes = (size_t)4 * FPW * 128;
+    FPS_CUDA(cudaMemsetAsync(static_cast<int8_t*>(gram_planes) + (slabs - 1) * slab_bytes, 0, slab_bytes, st));
+  }
+  if (int rc = features_run(ctx, x, y, n, H, DH, ld, tc ? xdh : nullptr, fused ? static_cast<int8_t*>(gram_planes) : nullptr,
+                            tc ? 1 : 0, st))
+    return rc;
+  if (!tc && n > 0) {
+    // fp32 cross-check engine: snap H in a separate pass
+    if (int rc = xop_snap(H, ld, n, FP, xh, st)) return rc;
+  }
+  if (h_planes_written) *h_planes_written = fused ? 1 : 0;
+  return 0;
+}
+
 // The exact int8 tensor-core path (gram_i8.cu) serves the Gram and the batched projection from the same row
 // count on, so that both always see the same (snapped) DH.  FPS_GRAM_I8=0 disables it, FPS_GRAM_I8_MIN moves
 // the threshold (tests).
+static int64_t exact_min_rows() {
+  static const int64_t i8_min = getenv("FPS_GRAM_I8_MIN") ? atoll(getenv("FPS_GRAM_I8_MIN")) : 16384;
+  return i8_min;
+}
 static bool use_i8(int64_t n) {
   static const int i8 = getenv("FPS_GRAM_I8") ? atoi(getenv("FPS_GRAM_I8")) : 1;
-  static const int64_t i8_min = getenv("FPS_GRAM_I8_MIN") ? atoll(getenv("FPS_GRAM_I8_MIN")) : 16384;
-  return i8 && n >= i8_min;
+  return i8 && n >= exact_min_rows();
 }
 
 int fps_gram_accum(fps_ctx* ctx, float* A, int64_t n, int64_t ld, double* G64, void* stream) {
@@ -364,7 +496,18 @@ int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, co
                         int* info, void* stream) {
   FPS_REQUIRE(ctx && G64 && Gbc64 && s64 && h_lambdas && L64 && info && n_lambda > 0, "fps_assemble_factor: bad argument");
   ProfScope ps(ctx, FPS_PROF_FACTOR, (cudaStream_t)stream);
-  return launch_assemble_factor(ctx, G64, Gbc64, s64, n_total, nbc_total, h_lambdas, h_jitter, n_lambda, L64, info,
+  return launch_assemble_factor(ctx, G64, Gbc64, s64, n_total, nbc_total, nullptr, h_lambdas, h_jitter, n_lambda, L64, info,
+                                (cudaStream_t)stream);
+}
+
+int fps_assemble_factor_packed(fps_ctx* ctx, const double* pack64, const double* h_lambdas, const double* h_jitter,
+                               int n_lambda, double* L64, int* info, void* stream) {
+  FPS_REQUIRE(ctx && pack64 && h_lambdas && L64 && info && n_lambda > 0, "fps_assemble_factor_packed: bad argument");
+  ProfScope ps(ctx, FPS_PROF_FACTOR, (cudaStream_t)stream);
+  const double* G = pack64;
+  const double* Gbc = pack64 + (size_t)FP * FP;
+  const double* sv = pack64 + 2 * (size_t)FP * FP;
+  return launch_assemble_factor(ctx, G, Gbc, sv, 0, 0, sv + FP, h_lambdas, h_jitter, n_lambda, L64, info,
                                 (cudaStream_t)stream);
 }
 
@@ -401,6 +544,65 @@ int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double*
 int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream) {
   FPS_REQUIRE(ctx && pred && ref && loss64 && n > 0, "fps_mse: bad argument");
   return launch_mse(pred, ref, n, loss64, (cudaStream_t)stream);
+}
+
+int fps_sse_columns(fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr, const double* ref_const,
+                    int64_t n, int B, double* sse64, void* stream) {
+  FPS_REQUIRE(ctx && pred && (ref || ref_const) && sse64 && ldp >= B && (ref_const || ldr >= B), "fps_sse_columns: bad argument");
+  return launch_sse_columns(ctx, pred, ldp, ref, ldr, ref_const, n, B, sse64, (cudaStream_t)stream);
+}
+int fps_sse_columns_f64(fps_ctx* ctx, const double* pred, int64_t ldp, const double* ref, int64_t ldr,
+                        const double* ref_const, int64_t n, int B, double* sse64, void* stream) {
+  FPS_REQUIRE(ctx && pred && (ref || ref_const) && sse64 && ldp >= B && (ref_const || ldr >= B), "fps_sse_columns_f64: bad argument");
+  return launch_sse_columns_d(ctx, pred, ldp, ref, ldr, ref_const, n, B, sse64, (cudaStream_t)stream);
+}
+
+// ---- cached exact-engine operands (caller-owned descriptors and digit planes) -----------------------------------------
+int64_t fps_exact_min_rows(void) { return use_i8((int64_t)1 << 62) ? exact_min_rows() : ((int64_t)1 << 62); }
+size_t fps_gram_planes_bytes(int64_t n) { return gram_planes_bytes(n); }
+size_t fps_recon_planes_bytes(int64_t n) { return recon_planes_bytes(n); }
+
+int fps_reserve_workspace(fps_ctx* ctx, int64_t n, int B) {
+  FPS_REQUIRE(ctx && n >= 0 && B >= 0, "fps_reserve_workspace: bad argument");
+  if (n <= 0 || !use_i8(n)) return 0;
+  if (int rc = gram_i8_reserve(ctx, n, B)) return rc;
+  return recon_i8_reserve(ctx, B);
+}
+
+int fps_gram_accum_x(fps_ctx* ctx, float* A, int64_t n, int64_t ld, void* xop, void* planes, int planes_written,
+                     double* G64, void* stream) {
+  FPS_REQUIRE(ctx && A && xop && planes && G64, "fps_gram_accum_x: null argument");
+  FPS_REQUIRE(ld >= FP && (uintptr_t)planes % 16 == 0, "fps_gram_accum_x: bad leading dimension / alignment");
+  ProfScope ps(ctx, FPS_PROF_GRAM, (cudaStream_t)stream);
+  return launch_gram_x(ctx, A, ld, n, static_cast<Xop*>(xop), static_cast<int8_t*>(planes), planes_written != 0, G64, FP,
+                       (cudaStream_t)stream);
+}
+
+int fps_project_rhs_x(fps_ctx* ctx, const void* xop, const void* planes, int64_t n, const float* Fm, int64_t ldf, int B,
+                      double* R64, int64_t ldr, void* stream) {
+  FPS_REQUIRE(ctx && xop && planes && Fm && R64, "fps_project_rhs_x: null argument");
+  FPS_REQUIRE(ldf >= B && ldr >= B, "fps_project_rhs_x: bad leading dimension");
+  ProfScope ps(ctx, FPS_PROF_PROJECT, (cudaStream_t)stream);
+  return launch_project_x(ctx, static_cast<const Xop*>(xop), static_cast<const int8_t*>(planes), n, Fm, ldf, B, R64, ldr,
+                          (cudaStream_t)stream);
+}
+
+int fps_recon_planes_build(fps_ctx* ctx, float* A, int64_t n, int64_t ld, void* xop, int derive_grid, void* planes,
+                           void* stream) {
+  FPS_REQUIRE(ctx && A && xop && planes, "fps_recon_planes_build: null argument");
+  FPS_REQUIRE(ld >= FP && ld % 4 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)planes % 16 == 0,
+              "fps_recon_planes_build: bad leading dimension / alignment");
+  return launch_recon_planes_build(ctx, A, ld, n, static_cast<Xop*>(xop), static_cast<int8_t*>(planes), derive_grid != 0,
+                                   (cudaStream_t)stream);
+}
+
+int fps_reconstruct_x(fps_ctx* ctx, const void* xop, const void* planes, int64_t n, const double* W64, int64_t ldw,
+                      const double* bias64, int B, float* out, int64_t ldo, void* stream) {
+  FPS_REQUIRE(ctx && xop && planes && W64 && out, "fps_reconstruct_x: null argument");
+  FPS_REQUIRE(ldw >= B && ldo >= B, "fps_reconstruct_x: bad leading dimension");
+  ProfScope ps(ctx, FPS_PROF_RECONSTRUCT, (cudaStream_t)stream);
+  return launch_recon_x(ctx, static_cast<const Xop*>(xop), static_cast<const int8_t*>(planes), n, W64, ldw, bias64, B, out,
+                        ldo, (cudaStream_t)stream);
 }
 
 // ---- fp64 engine entry points (precision = float64) ----------------------------------------------

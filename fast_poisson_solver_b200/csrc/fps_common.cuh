@@ -57,6 +57,21 @@ struct StreamScale {  // per-stream power-of-two scales of one layer's input pla
   float s[4];
 };
 
+// Exact-operand descriptor ("xop", FPS_XOP_BYTES of caller- or context-owned device memory): the per-column fixed-point
+// grid on which one fp32 feature matrix A (n x ld) enters the int8 engine (gram_i8.cu, recon_i8.cu).
+//   exps[f]   e_f with |A[:, f]| < 2^e_f          scale[f] = {2^(30 - e_f), 2^(e_f - 30)}
+//   cmax[f]   max |A[:, f]| as float bits (atomicMax), recorded by the kernel that produced A
+//   flags[0]  set by the fused last-layer epilogue when an element did not fit the calibrated grid: the consumers then
+//             rebuild exps from cmax and re-split A (device-side conditional, no host round trip)
+constexpr int XOP_ROWS = 768;
+struct Xop {
+  int exps[XOP_ROWS];
+  float2 scale[XOP_ROWS];
+  unsigned cmax[XOP_ROWS];
+  int flags[4];
+};
+static_assert(sizeof(Xop) <= FPS_XOP_BYTES, "Xop must fit FPS_XOP_BYTES");
+
 }  // namespace fps
 
 namespace fps {
@@ -82,9 +97,12 @@ struct fps_ctx {
   int* tc_sched;          // 2 ints for the dynamic tile scheduler of layer_tc_pair_kernel (zero between launches)
   void* gi_state;         // int8 exact-Gram workspace, owned by gram_i8.cu (allocated on first use)
   void* ri_state;         // int8 reconstruction workspace, owned by recon_i8.cu (allocated on first use)
-  unsigned* dh_cmax;      // FPW words: per-feature max |DH| (float bits) of the last fps_features call (tcgen05 engine)
-  const float* dh_cmax_of;  // the DH buffer those maxima describe (null: none), and its row count
-  int64_t dh_cmax_n;
+  fps::Xop* xop_tmp;      // context-owned descriptors for the uncached entry points: [0] A operand, [1] scratch
+  unsigned* dh_cal_cmax;  // FPW words: max |DH| per feature over the calibration sample (float bits); 0 = not calibrated
+  int dh_cal_valid;
+  int gain_checked;       // the accumulator-gain compensation of layer_tc.cu has been checked against the fp32 engine
+  int gain_off;           // 1: compensation disabled for this weight set (the check found it harmful)
+  double cal_err[4];      // rel-L2 vs the fp32 engine on the calibration sample: {H, DH} with gain, {H, DH} without
   double* w64[fps::NLAYER]; // fp64 engine: (FP, Kp) row-major weights, zero padded
   double* b64[fps::NLAYER]; // fp64 engine: (FP) biases
 };
@@ -118,9 +136,21 @@ int launch_fourier(const fps_ctx* ctx, const double* x, const double* y, int64_t
 // last = write H (and DH when streams == 4) instead of the next layer's planes.
 int launch_layer_simt(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int64_t points, int streams,
                       bool last, float* H, float* DH, int64_t ld, cudaStream_t st);
+// Exact-engine outputs of the LAST layer of a PDE-point wave (tcgen05 engine; all null = plain fp32 H / DH):
+//   xdh      grid of DH.  Its cmax always receives max |DH| per feature.  With gplanes != null the epilogue snaps DH to
+//            the grid already stored in xdh->scale (calibrated, set by the caller), writes the point-major digit planes
+//            of gram_i8.cu for the points [point0, point0 + points) and raises xdh->flags[0] if an element does not fit.
+//   snap_h   snap H to the uniform 2^-30 grid (|H| <= 1: no maxima needed, cannot overflow)
+struct FusedOut {
+  Xop* xdh;
+  int8_t* gplanes;
+  int64_t point0;
+  int snap_h;
+};
 int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int64_t points, int streams,
-                    bool last, float* H, float* DH, int64_t ld, cudaStream_t st);
+                    bool last, float* H, float* DH, int64_t ld, const FusedOut* fused, cudaStream_t st);
 int tc_init(fps_ctx* ctx);
+int chol_init(fps_ctx* ctx);
 void tc_destroy(fps_ctx* ctx);
 
 // C (M x Ncols, ldc) fp64 += A^T B over n rows; A (n, lda) fp32 M columns, B (n, ldb) fp32 Ncols columns.
@@ -129,6 +159,25 @@ int launch_atb_f64(const fps_ctx* ctx, const float* A, int64_t lda, int M, const
                    int64_t n, double* C, int64_t ldc, bool symmetric, cudaStream_t st);
 // Same Gram (symmetric A^T A, M = FP) on the int8 tensor cores with exact products (gram_i8.cu)
 int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, int64_t ldg, cudaStream_t st);
+// cached forms: caller-owned descriptor + digit planes of all n rows (gram_i8.cu, recon_i8.cu)
+size_t gram_planes_bytes(int64_t n);
+size_t recon_planes_bytes(int64_t n);
+int launch_gram_x(fps_ctx* ctx, float* A, int64_t lda, int64_t n, Xop* x, int8_t* planes, bool fused, double* G,
+                  int64_t ldg, cudaStream_t st);
+int launch_project_x(fps_ctx* ctx, const Xop* x, const int8_t* planes, int64_t n, const float* F, int64_t ldf, int B,
+                     double* R, int64_t ldr, cudaStream_t st);
+int launch_recon_planes_build(fps_ctx* ctx, float* A, int64_t lda, int64_t n, Xop* x, int8_t* planes, bool need_grid,
+                              cudaStream_t st);
+int launch_recon_x(fps_ctx* ctx, const Xop* x, const int8_t* planes, int64_t n, const double* W, int64_t ldw,
+                   const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
+int gram_i8_reserve(fps_ctx* ctx, int64_t n, int B);
+int recon_i8_reserve(fps_ctx* ctx, int B);
+// xop.cu
+int xop_colmax(const fps_ctx* ctx, const float* A, int64_t lda, int64_t n, int ncols, unsigned* cmax, cudaStream_t st);
+int xop_exps(const unsigned* cmax, int ncols, int rows, int headroom, int* exps, float2* scale, const int* cond,
+             cudaStream_t st);
+int xop_uniform(Xop* x, int e, cudaStream_t st);
+int xop_snap(float* A, int64_t lda, int64_t n, int ncols, const Xop* x, cudaStream_t st);
 int launch_project_i8(fps_ctx* ctx, float* DH, int64_t lda, const float* F, int64_t ldf, int B, int64_t n, double* R,
                       int64_t ldr, cudaStream_t st);
 void gram_i8_destroy(fps_ctx* ctx);
@@ -138,13 +187,17 @@ int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double
 void recon_i8_destroy(fps_ctx* ctx);
 int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream_t st);
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
-                           int64_t nbc_total, const double* h_lambdas, const double* h_jitter, int n_lambda, double* L, int* info,
-                           cudaStream_t st);
+                           int64_t nbc_total, const double* d_counts, const double* h_lambdas, const double* h_jitter,
+                           int n_lambda, double* L, int* info, cudaStream_t st);
 int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
                           const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st);
 int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
                        const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
 int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st);
+int launch_sse_columns(const fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr,
+                       const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st);
+int launch_sse_columns_d(const fps_ctx* ctx, const double* pred, int64_t ldp, const double* ref, int64_t ldr,
+                         const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st);
 
 // count `n` kernel launches (instrumentation for bench.py's gpu_launches)
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }

@@ -645,6 +645,68 @@ __global__ void mse_kernel(const float* __restrict__ pred, const float* __restri
   }
 }
 
+// Batched form (multi-lambda sweep over B right-hand sides): sse[j] += sum_i (pred[i][j] - ref[i][j])^2.
+// CTA = 32 columns x 8 row lanes over one row chunk; partial sums per chunk go to the split-K workspace and are summed in
+// chunk order (bit-reproducible).  ref_const: one reference value per column instead of a matrix.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sse_columns_kernel(const T* __restrict__ pred, int64_t ldp, const T* __restrict__ ref, int64_t ldr,
+                   const double* __restrict__ ref_const, int64_t n, int B, int64_t rows_per_chunk,
+                   double* __restrict__ partial) {
+  __shared__ double red[8][33];
+  const int cl = threadIdx.x % 32, rl = threadIdx.x / 32;
+  const int j = blockIdx.x * 32 + cl;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
+  double s = 0.0;
+  if (j < B) {
+    const double rc = ref_const ? ref_const[j] : 0.0;
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      const double d = (double)pred[r * ldp + j] - (ref_const ? rc : (double)ref[r * ldr + j]);
+      s = fma(d, d, s);
+    }
+  }
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && j < B) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += red[q][cl];
+    partial[(size_t)blockIdx.y * B + j] = s;
+  }
+}
+
+__global__ void sse_reduce_kernel(const double* __restrict__ partial, int chunks, int B, double* __restrict__ sse) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= B) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * B + j];
+  sse[j] += s;
+}
+
+template <typename T>
+static int launch_sse_columns_t(const fps_ctx* ctx, const T* pred, int64_t ldp, const T* ref, int64_t ldr,
+                                const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  int64_t chunks = std::min<int64_t>({(int64_t)512, (n + 63) / 64, (int64_t)(ctx->partial_bytes / ((size_t)B * sizeof(double)))});
+  FPS_REQUIRE(chunks >= 1, "sse_columns: %d columns exceed the partial workspace", B);
+  const int64_t rpc = (n + chunks - 1) / chunks;
+  chunks = (n + rpc - 1) / rpc;
+  sse_columns_kernel<T><<<dim3((unsigned)((B + 31) / 32), (unsigned)chunks), 256, 0, st>>>(pred, ldp, ref, ldr, ref_const, n, B,
+                                                                                          rpc, ctx->partial);
+  sse_reduce_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->partial, (int)chunks, B, sse);
+  count_launch(2);
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_sse_columns(const fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr,
+                       const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st) {
+  return launch_sse_columns_t<float>(ctx, pred, ldp, ref, ldr, ref_const, n, B, sse, st);
+}
+int launch_sse_columns_d(const fps_ctx* ctx, const double* pred, int64_t ldp, const double* ref, int64_t ldr,
+                         const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st) {
+  return launch_sse_columns_t<double>(ctx, pred, ldp, ref, ldr, ref_const, n, B, sse, st);
+}
+
 int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st) {
   mse_kernel<<<1, 1024, 0, st>>>(pred, ref, n, loss);
   count_launch();

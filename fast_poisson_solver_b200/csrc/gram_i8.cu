@@ -5,7 +5,8 @@
 // projection uses (measured on the CPU oracle, G = 32: a Gram that is off by 1e-11 costs 1e-4 in u).  The fp64
 // pipe gives 35 TFLOP/s, the int8 tensor pipe 4.5 POP/s.
 //
-//   1. gi_colmax_kernel     per-column max |a|  ->  exponent e_f with |a[:, f]| < 2^e_f
+//   1. xop.cu               per-column max |a|  ->  exponent e_f with |a[:, f]| < 2^e_f (or the calibrated grid of
+//                           the fused feature epilogue, layer_tc.cu)
 //   2. gi_split_kernel      X = rint(a * 2^(30 - e_f)), a 31-bit integer.  For |a| >= 2^(e_f - 7) this is a itself;
 //                           smaller elements move by < 2^-31 of the column maximum (< 1 % of one fp32 ulp of that
 //                           maximum) and are SNAPPED IN PLACE: A is overwritten by X 2^(e_f - 30), which is again
@@ -21,9 +22,9 @@
 //   4. gi_reduce_kernel     G[r][c] += 2^(e_r + e_c - 12) * sum_splits sum_o 2^(-8 o) Acc_o   (fixed order, fp64)
 //
 // The same engine computes the batched RHS projection R += DH^T F (solver.py:197 + :301, launch_project_i8):
-// A = the digit planes of DH (rebuilt per call: the grid only depends on the column maxima, so a DH that went
-// through the Gram is left untouched), B = digit planes of F (a copy on the grid of each right-hand side; F itself
-// is not modified), rectangular tiling 3 x ceil(B / 64).
+// A = the digit planes of DH (the SAME planes the Gram used when the caller keeps them, launch_project_x; rebuilt per
+// call otherwise), B = digit planes of F (a copy on the grid of each right-hand side; F itself is not modified),
+// rectangular tiling 3 x ceil(B / 64).
 //
 // Every product and every partial sum is an exact integer; the only rounding is the final fp64 combination
 // (2^-53 relative), so G is the Gram of the stored A to fp64 rounding, bit-reproducible and independent of the
@@ -61,48 +62,7 @@ __host__ __device__ inline void gi_tile(int t, int& I, int& J) {
   else { I = 2; J = t - 12; }
 }
 
-// ---- 1. column maxima -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-gi_colmax_kernel(const float* __restrict__ A, int64_t ld, int64_t n, int ncols, int64_t rows_per_cta,
-                 unsigned* __restrict__ cmax) {
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
-  for (int c0 = blockIdx.y * 768; c0 < min(ncols, (int)(blockIdx.y + 1) * 768); c0 += 768) {
-    const int t = c0 + threadIdx.x;
-    const bool h0 = t < ncols, h1 = t + 256 < ncols, h2 = t + 512 < ncols;
-    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-    for (int64_t r = r0; r < r1; r += 4) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (r + u < r1) {
-          const float* row = A + (r + u) * ld;
-          if (h0) m0 = fmaxf(m0, fabsf(__ldg(row + t)));
-          if (h1) m1 = fmaxf(m1, fabsf(__ldg(row + t + 256)));
-          if (h2) m2 = fmaxf(m2, fabsf(__ldg(row + t + 512)));
-        }
-      }
-    }
-    if (h0) atomicMax(cmax + t, __float_as_uint(m0));
-    if (h1) atomicMax(cmax + t + 256, __float_as_uint(m1));
-    if (h2) atomicMax(cmax + t + 512, __float_as_uint(m2));
-  }
-}
-
-// exponent e with max < 2^e, and the fixed-point scale 2^(30 - e) with its inverse (fp32 powers of two; e is
-// clamped to >= -90 so that both stay normal numbers: a column below 2^-90 is kept on a coarser grid)
-__global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int ncols, int rows, int* __restrict__ exps,
-                               float2* __restrict__ scale) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= rows) return;
-  int e = 0;
-  if (f < ncols) {
-    const unsigned bits = cmax[f];
-    const int E = (int)(bits >> 23);
-    e = bits ? ((E > 0 ? E : 1) - 126) : 0;
-    if (e < -90) e = -90;
-  }
-  exps[f] = e;
-  scale[f] = make_float2(ldexpf(1.0f, 30 - e), ldexpf(1.0f, e - 30));
-}
+// ---- 1. column maxima and exponents: xop.cu (shared with recon_i8.cu) --------------------------------
 
 // ---- 2. digit split + transpose -------------------------------------------------------------------
 // CTA = 128 points x 64 features.  Reads are coalesced along the feature axis, the digits go through shared
@@ -112,8 +72,9 @@ __global__ void gi_exps_kernel(const unsigned* __restrict__ cmax, int ncols, int
 template <bool SNAP>
 __global__ void __launch_bounds__(256)
 gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int rows, int slabs,
-                const float2* __restrict__ scale, int8_t* __restrict__ planes) {
+                const float2* __restrict__ scale, int8_t* __restrict__ planes, const int* __restrict__ cond) {
   __shared__ uint32_t sm[GI_SL][64][33];
+  if (cond && *cond == 0) return;   // overflow fallback of the fused feature epilogue: nothing to redo (whole CTA)
   const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int fh = w & 1, pq = w >> 1;
   const int fl = fh * 32 + lane;
@@ -400,18 +361,20 @@ gi_reduce_kernel(const double* __restrict__ partial, int nsplit, int ntiles, int
 }
 
 // ---- host -----------------------------------------------------------------------------------------
-struct GiPlanes {            // digit planes of one operand: planes[slab][digit][rows][128]
-  int8_t* data = nullptr;
-  size_t cap_bytes = 0;
-  unsigned* cmax = nullptr;  // rows_cap x {u32 cmax, i32 exps, float2 scale}
-  int* exps = nullptr;
-  float2* scale = nullptr;
-  int rows_cap = 0;
-  int rows = 0;              // feature rows per digit plane of the current contents
+struct GiOperand {           // digit planes of one operand, planes[slab][digit][rows][128], and its per-row grid
+  int8_t* data;
+  const int* exps;
+  const float2* scale;
+  int rows;                  // feature rows (A: 768) or right-hand sides rounded up to 64 (B) per digit plane
 };
 
 struct GiState {
-  GiPlanes a, b;
+  int8_t* a_data = nullptr;  // context-owned A planes (uncached entry points only)
+  size_t a_cap = 0;
+  int8_t* b_data = nullptr;  // digit planes of F (one projection pass)
+  size_t b_cap = 0;
+  unsigned* b_meta = nullptr;  // b_rows_cap x {u32 cmax, i32 exps, float2 scale}
+  int b_rows_cap = 0;
   double* partial = nullptr;
   size_t partial_bytes = 0;
   void* encode = nullptr;
@@ -421,16 +384,15 @@ typedef CUresult (*GiEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-constexpr int64_t GI_MAX_CHUNK = 1 << 20;          // points per Gram pass: 3 GiB of digit planes
+constexpr int64_t GI_MAX_CHUNK = 1 << 20;          // points per pass through context-owned planes: 3 GiB
 constexpr size_t GI_B_PLANE_BYTES = (size_t)5 << 30;  // budget for the digit planes of F per projection pass
 
 void gram_i8_destroy(fps_ctx* ctx) {
   GiState* s = static_cast<GiState*>(ctx->gi_state);
   if (!s) return;
-  cudaFree(s->a.data);
-  cudaFree(s->a.cmax);
-  cudaFree(s->b.data);
-  cudaFree(s->b.cmax);
+  cudaFree(s->a_data);
+  cudaFree(s->b_data);
+  cudaFree(s->b_meta);
   cudaFree(s->partial);
   delete s;
   ctx->gi_state = nullptr;
@@ -451,21 +413,27 @@ static int gi_state_get(fps_ctx* ctx, GiState** out) {
   return 0;
 }
 
-// grow-only buffers; workspace_bytes follows
-static int gi_reserve_planes(fps_ctx* ctx, GiPlanes& pl, int rows, int64_t points) {
-  const size_t need = (size_t)GI_SL * rows * ((points + GI_SLAB - 1) / GI_SLAB * GI_SLAB);
-  if (need > pl.cap_bytes) {
-    if (pl.data) { FPS_CUDA(cudaFree(pl.data)); ctx->workspace_bytes -= pl.cap_bytes; pl.data = nullptr; pl.cap_bytes = 0; }
-    FPS_CUDA(cudaMalloc(&pl.data, need));
-    pl.cap_bytes = need;
-    ctx->workspace_bytes += need;
-  }
-  if (rows > pl.rows_cap) {
-    if (pl.cmax) FPS_CUDA(cudaFree(pl.cmax));
-    FPS_CUDA(cudaMalloc(&pl.cmax, (size_t)rows * (sizeof(unsigned) + sizeof(int) + sizeof(float2))));
-    pl.scale = reinterpret_cast<float2*>(pl.cmax + 2 * (size_t)rows);   // 8-byte aligned: rows is a multiple of 64
-    pl.exps = reinterpret_cast<int*>(pl.cmax + rows);
-    pl.rows_cap = rows;
+static size_t gi_plane_bytes(int rows, int64_t points) {
+  return (size_t)GI_SL * rows * ((points + GI_SLAB - 1) / GI_SLAB * GI_SLAB);
+}
+
+// grow-only context-owned buffers (workspace_bytes follows).  Growing frees and reallocates, which synchronises the
+// device: fps_reserve_workspace sizes them up front so that nothing allocates mid-stream.
+static int gi_grow(fps_ctx* ctx, int8_t** buf, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*buf) { FPS_CUDA(cudaFree(*buf)); ctx->workspace_bytes -= *cap; *buf = nullptr; *cap = 0; }
+  FPS_CUDA(cudaMalloc(buf, need));
+  *cap = need;
+  ctx->workspace_bytes += need;
+  return 0;
+}
+
+static int gi_reserve_b(fps_ctx* ctx, GiState* s, int rows_b, int64_t points) {
+  if (int rc = gi_grow(ctx, &s->b_data, &s->b_cap, gi_plane_bytes(rows_b, points))) return rc;
+  if (rows_b > s->b_rows_cap) {
+    if (s->b_meta) FPS_CUDA(cudaFree(s->b_meta));
+    FPS_CUDA(cudaMalloc(&s->b_meta, (size_t)rows_b * (sizeof(unsigned) + sizeof(int) + sizeof(float2))));
+    s->b_rows_cap = rows_b;
   }
   return 0;
 }
@@ -481,25 +449,29 @@ static int gi_reserve_partial(fps_ctx* ctx, GiState* s, int nitems) {
   return 0;
 }
 
-// column maxima (unless `known` supplies them) -> exponents -> digit planes of `np` rows of A starting at slab 0
+// rows of one projection pass for B right-hand sides: max_chunk / 2^k points, the F planes within their budget
+static int64_t gi_project_chunk(int rows_b, int64_t n, int64_t max_chunk) {
+  int64_t chunk = max_chunk;
+  while ((size_t)GI_SL * rows_b * chunk > GI_B_PLANE_BYTES && chunk / 2 >= GI_SLAB) chunk /= 2;
+  return chunk > n ? n : chunk;
+}
+
+static int64_t gi_env_chunk() {
+  // FPS_GRAM_I8_CHUNK: points per pass (tests exercise the multi-pass loops with a small value)
+  static const int64_t v = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : GI_MAX_CHUNK;
+  return v;
+}
+
+// digit planes of `np` rows of A (starting at slab 0 of `planes`) on the grid `scale`; SNAP writes the grid values back
 template <bool SNAP>
-static int gi_split(fps_ctx* ctx, GiPlanes& pl, float* A, int64_t lda, int64_t np, int ncols, int rows,
-                    const unsigned* known, cudaStream_t st) {
-  if (!known) {
-    FPS_CUDA(cudaMemsetAsync(pl.cmax, 0, (size_t)rows * sizeof(unsigned), st));
-    int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (np + 63) / 64);
-    const int64_t rpc = ((np + ctas - 1) / ctas + 3) / 4 * 4;
-    ctas = (np + rpc - 1) / rpc;
-    gi_colmax_kernel<<<dim3((unsigned)ctas, (unsigned)((ncols + 767) / 768)), 256, 0, st>>>(A, lda, np, ncols, rpc, pl.cmax);
-    count_launch(1);
-  }
-  gi_exps_kernel<<<(rows + 255) / 256, 256, 0, st>>>(known ? known : pl.cmax, ncols, rows, pl.exps, pl.scale);
+static int gi_split(float* A, int64_t lda, int64_t np, int ncols, int rows, const float2* scale, int8_t* planes,
+                    const int* cond, cudaStream_t st) {
   const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
   FPS_REQUIRE(slabs <= (int64_t)65535 * 65535, "gram_i8: too many slabs");
   const unsigned gy = (unsigned)(slabs < 65535 ? slabs : 65535), gz = (unsigned)((slabs + 65534) / 65535);
-  gi_split_kernel<SNAP><<<dim3((unsigned)(rows / 64), gy, gz), 256, 0, st>>>(A, lda, np, ncols, rows, (int)slabs, pl.scale,
-                                                                              pl.data);
-  count_launch(2);
+  gi_split_kernel<SNAP><<<dim3((unsigned)(rows / 64), gy, gz), 256, 0, st>>>(A, lda, np, ncols, rows, (int)slabs, scale,
+                                                                              planes, cond);
+  count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -533,12 +505,22 @@ static int gi_pick_split(int ntiles, int slabs, int pairs) {
   return best;
 }
 
-// one pass: C (M x Nc, ldc) += A^T B over the `slabs` 128-point slabs that start at slab_a0 of the A planes and at 0
-// of the B planes
-static int gi_run(fps_ctx* ctx, GiState* s, const GiPlanes& pa, int64_t slabs_in_a, int slab_a0, const GiPlanes& pb,
+static int gi_nitems(int ntiles, int64_t slabs128, int pairs, int rb, int* slabs_total, int* slabs_per_split) {
+  *slabs_total = (int)(slabs128 * (GI_SLAB / rb));
+  int nsplit = gi_pick_split(ntiles, *slabs_total, pairs);
+  *slabs_per_split = (*slabs_total + nsplit - 1) / nsplit;
+  nsplit = (*slabs_total + *slabs_per_split - 1) / *slabs_per_split;
+  return ntiles * nsplit;
+}
+
+// one pass: C (M x Nc, ldc) += A^T B over the `slabs` 128-point slabs that start at slab_a0 of the A planes (which hold
+// slabs_in_a slabs) and at 0 of the B planes
+static int gi_run(fps_ctx* ctx, GiState* s, const GiOperand& pa, int64_t slabs_in_a, int64_t slab_a0, const GiOperand& pb,
                   int64_t slabs_in_b, int64_t slabs, bool sym, int M, int Nc, double* C, int64_t ldc, cudaStream_t st) {
   static const int rb = getenv("FPS_GRAM_ROWB") ? atoi(getenv("FPS_GRAM_ROWB")) : 128;
   FPS_REQUIRE(rb == 64 || rb == 128, "FPS_GRAM_ROWB must be 64 or 128");
+  FPS_REQUIRE(slabs_in_a * GI_SL * pa.rows < ((int64_t)1 << 31) && slabs * (GI_SLAB / rb) < ((int64_t)1 << 31),
+              "gram_i8: %lld slabs exceed the 32-bit tile coordinates", (long long)slabs_in_a);
   CUtensorMap tmA, tmB;
   if (gi_make_map(s, &tmA, pa.data, slabs_in_a, pa.rows, GI_TM, rb)) return 2;
   if (gi_make_map(s, &tmB, pb.data, slabs_in_b, pb.rows, GI_TN, rb)) return 2;
@@ -548,13 +530,10 @@ static int gi_run(fps_ctx* ctx, GiState* s, const GiPlanes& pa, int64_t slabs_in
   P.ntiles = sym ? GI_NTILES : 3 * P.tiles_j;
   P.rows_a = pa.rows;
   P.rows_b = pb.rows;
-  P.slab_a0 = slab_a0;
-  P.slabs_total = (int)(slabs * (GI_SLAB / rb));
+  P.slab_a0 = (int)slab_a0;
   const int pairs = ctx->sm_count / 2;
-  int nsplit = gi_pick_split(P.ntiles, P.slabs_total, pairs);
-  P.slabs_per_split = (P.slabs_total + nsplit - 1) / nsplit;
-  nsplit = (P.slabs_total + P.slabs_per_split - 1) / P.slabs_per_split;
-  P.nitems = P.ntiles * nsplit;
+  P.nitems = gi_nitems(P.ntiles, slabs, pairs, rb, &P.slabs_total, &P.slabs_per_split);
+  const int nsplit = P.nitems / P.ntiles;
   if (int rc = gi_reserve_partial(ctx, s, P.nitems)) return rc;
   P.partial = s->partial;
   const int groups = P.nitems < pairs ? P.nitems : pairs;
@@ -568,62 +547,128 @@ static int gi_run(fps_ctx* ctx, GiState* s, const GiPlanes& pa, int64_t slabs_in
   return 0;
 }
 
-// G (FP x FP, ldg) += A^T A over n rows of A (n x >= FP, lda), lower triangle computed and mirrored.
-// A is snapped in place to the per-column fixed-point grid (see the header).
-int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, int64_t ldg, cudaStream_t st) {
+size_t gram_planes_bytes(int64_t n) { return n > 0 ? gi_plane_bytes(GI_ROWS, n) : 0; }
+
+// ---- cached form: the caller owns the descriptor `x` and the digit planes of ALL n rows ------------------------------
+// G (FP x FP, ldg) += A^T A.  fused: the feature kernel has already written planes, snapped A and the calibrated grid
+// into x (layer_tc.cu epilogue); only if it raised x->flags[0] (an element beyond the calibrated grid) are the
+// exponents rebuilt from the recorded maxima and A re-split - both kernels are launched either way and return at once
+// when there is nothing to do, so no host round trip is needed.  !fused: column maxima, exponents and split run here.
+int launch_gram_x(fps_ctx* ctx, float* A, int64_t lda, int64_t n, Xop* x, int8_t* planes, bool fused, double* G,
+                  int64_t ldg, cudaStream_t st) {
   if (n <= 0) return 0;
-  // FPS_GRAM_I8_CHUNK: points per pass (tests exercise the multi-pass loop with a small value)
-  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : GI_MAX_CHUNK;
-  FPS_REQUIRE(max_chunk >= GI_SLAB && (max_chunk & (max_chunk - 1)) == 0, "FPS_GRAM_I8_CHUNK must be a power of two >= 128");
-  const int64_t chunk = n < max_chunk ? n : max_chunk;
   GiState* s;
   if (int rc = gi_state_get(ctx, &s)) return rc;
-  if (int rc = gi_reserve_planes(ctx, s->a, GI_ROWS, chunk)) return rc;
-  // column maxima: recorded by the feature kernel when A is the DH it has just produced (a bound over all n rows
-  // is valid for every chunk), else one streaming pass per chunk
-  const bool have_cmax = ctx->dh_cmax_of == A && ctx->dh_cmax_n == n;
+  const int* cond = nullptr;
+  if (fused) {
+    cond = &x->flags[0];
+  } else {
+    if (int rc = xop_colmax(ctx, A, lda, n, FP, x->cmax, st)) return rc;
+  }
+  if (int rc = xop_exps(x->cmax, FP, GI_ROWS, 0, x->exps, x->scale, cond, st)) return rc;
+  if (int rc = gi_split<true>(A, lda, n, FP, GI_ROWS, x->scale, planes, cond, st)) return rc;
+  const int64_t slabs = (n + GI_SLAB - 1) / GI_SLAB;
+  const GiOperand op{planes, x->exps, x->scale, GI_ROWS};
+  return gi_run(ctx, s, op, slabs, 0, op, slabs, slabs, true, FP, FP, G, ldg, st);
+}
+
+// R (FP x B, ldr) += DH^T F from the cached planes of DH; F (n x B, ldf) is read only (its digit planes, on the grid of
+// each right-hand side per pass, live in the context workspace)
+int launch_project_x(fps_ctx* ctx, const Xop* x, const int8_t* planes, int64_t n, const float* F, int64_t ldf, int B,
+                     double* R, int64_t ldr, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  GiState* s;
+  if (int rc = gi_state_get(ctx, &s)) return rc;
+  const int rows_b = (B + 63) / 64 * 64;
+  const int64_t chunk = gi_project_chunk(rows_b, n, GI_MAX_CHUNK);
+  if (int rc = gi_reserve_b(ctx, s, rows_b, chunk)) return rc;
+  unsigned* b_cmax = s->b_meta;
+  int* b_exps = reinterpret_cast<int*>(s->b_meta + s->b_rows_cap);
+  float2* b_scale = reinterpret_cast<float2*>(s->b_meta + 2 * (size_t)s->b_rows_cap);   // 8-byte aligned: rows % 64 == 0
+  const int64_t slabs_all = (n + GI_SLAB - 1) / GI_SLAB;
+  const GiOperand pa{const_cast<int8_t*>(planes), x->exps, x->scale, GI_ROWS};
+  const GiOperand pb{s->b_data, b_exps, b_scale, rows_b};
   for (int64_t p0 = 0; p0 < n; p0 += chunk) {
     const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
-    s->a.rows = GI_ROWS;
-    if (int rc = gi_split<true>(ctx, s->a, A + p0 * lda, lda, np, FP, GI_ROWS, have_cmax ? ctx->dh_cmax : nullptr, st))
-      return rc;
     const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
-    if (int rc = gi_run(ctx, s, s->a, slabs, 0, s->a, slabs, slabs, true, FP, FP, G, ldg, st)) return rc;
+    float* Fc = const_cast<float*>(F) + p0 * ldf;
+    if (int rc = xop_colmax(ctx, Fc, ldf, np, B, b_cmax, st)) return rc;
+    if (int rc = xop_exps(b_cmax, B, rows_b, 0, b_exps, b_scale, nullptr, st)) return rc;
+    if (int rc = gi_split<false>(Fc, ldf, np, B, rows_b, b_scale, s->b_data, nullptr, st)) return rc;
+    if (int rc = gi_run(ctx, s, pa, slabs_all, p0 / GI_SLAB, pb, slabs, slabs, false, FP, B, R, ldr, st)) return rc;
   }
   return 0;
 }
 
-// R (FP x B, ldr) += DH^T F over n rows; DH (n x >= FP, lda) is snapped in place like in launch_gram_i8 (a no-op
-// when the Gram has already done it: the grid only depends on the column maxima), F (n x B, ldf) is read only.
-// The digit planes of DH are rebuilt here rather than cached from the Gram: 1.5 ms per 2^20 points buys
-// independence from what happened to the buffer in between.
+// ---- uncached forms (fps_gram_accum / fps_project_rhs on any matrix): planes in the context workspace, passes of at
+// most 2^20 points, ONE grid for all n rows (column maxima over the whole matrix first) --------------------------------
+int launch_gram_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, double* G, int64_t ldg, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int64_t max_chunk = gi_env_chunk();
+  FPS_REQUIRE(max_chunk >= GI_SLAB && (max_chunk & (max_chunk - 1)) == 0, "FPS_GRAM_I8_CHUNK must be a power of two >= 128");
+  const int64_t chunk = n < max_chunk ? n : max_chunk;
+  GiState* s;
+  if (int rc = gi_state_get(ctx, &s)) return rc;
+  if (int rc = gi_grow(ctx, &s->a_data, &s->a_cap, gi_plane_bytes(GI_ROWS, chunk))) return rc;
+  Xop* x = ctx->xop_tmp;
+  if (int rc = xop_colmax(ctx, A, lda, n, FP, x->cmax, st)) return rc;
+  if (int rc = xop_exps(x->cmax, FP, GI_ROWS, 0, x->exps, x->scale, nullptr, st)) return rc;
+  const GiOperand op{s->a_data, x->exps, x->scale, GI_ROWS};
+  for (int64_t p0 = 0; p0 < n; p0 += chunk) {
+    const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
+    if (int rc = gi_split<true>(A + p0 * lda, lda, np, FP, GI_ROWS, x->scale, s->a_data, nullptr, st)) return rc;
+    const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
+    if (int rc = gi_run(ctx, s, op, slabs, 0, op, slabs, slabs, true, FP, FP, G, ldg, st)) return rc;
+  }
+  return 0;
+}
+
 int launch_project_i8(fps_ctx* ctx, float* DH, int64_t lda, const float* F, int64_t ldf, int B, int64_t n, double* R,
                       int64_t ldr, cudaStream_t st) {
   if (n <= 0 || B <= 0) return 0;
   GiState* s;
   if (int rc = gi_state_get(ctx, &s)) return rc;
   const int rows_b = (B + 63) / 64 * 64;
-  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : GI_MAX_CHUNK;
+  const int64_t max_chunk = gi_env_chunk();
   FPS_REQUIRE(max_chunk >= GI_SLAB && (max_chunk & (max_chunk - 1)) == 0, "FPS_GRAM_I8_CHUNK must be a power of two >= 128");
-  // Passes of max_chunk / 2^k points: pass boundaries nest inside the Gram's passes, so a pass never mixes rows that
-  // the Gram snapped on different grids (its column maxima can only be smaller -> a finer grid -> DH is unchanged).
-  int64_t chunk = max_chunk;
-  while ((size_t)GI_SL * rows_b * chunk > GI_B_PLANE_BYTES && chunk / 2 >= GI_SLAB) chunk /= 2;
-  if (chunk > n) chunk = n;
-  if (int rc = gi_reserve_planes(ctx, s->a, GI_ROWS, chunk)) return rc;
-  if (int rc = gi_reserve_planes(ctx, s->b, rows_b, chunk)) return rc;
-  s->a.rows = GI_ROWS;
-  s->b.rows = rows_b;
-  const bool have_cmax = ctx->dh_cmax_of == DH && ctx->dh_cmax_n == n;
+  const int64_t chunk = gi_project_chunk(rows_b, n, max_chunk);
+  if (int rc = gi_grow(ctx, &s->a_data, &s->a_cap, gi_plane_bytes(GI_ROWS, chunk))) return rc;
+  if (int rc = gi_reserve_b(ctx, s, rows_b, chunk)) return rc;
+  unsigned* b_cmax = s->b_meta;
+  int* b_exps = reinterpret_cast<int*>(s->b_meta + s->b_rows_cap);
+  float2* b_scale = reinterpret_cast<float2*>(s->b_meta + 2 * (size_t)s->b_rows_cap);
+  Xop* x = ctx->xop_tmp;
+  if (int rc = xop_colmax(ctx, DH, lda, n, FP, x->cmax, st)) return rc;
+  if (int rc = xop_exps(x->cmax, FP, GI_ROWS, 0, x->exps, x->scale, nullptr, st)) return rc;
+  const GiOperand pa{s->a_data, x->exps, x->scale, GI_ROWS};
+  const GiOperand pb{s->b_data, b_exps, b_scale, rows_b};
   for (int64_t p0 = 0; p0 < n; p0 += chunk) {
     const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
     const int64_t slabs = (np + GI_SLAB - 1) / GI_SLAB;
-    if (int rc = gi_split<true>(ctx, s->a, DH + p0 * lda, lda, np, FP, GI_ROWS, have_cmax ? ctx->dh_cmax : nullptr, st))
-      return rc;
-    if (int rc = gi_split<false>(ctx, s->b, const_cast<float*>(F) + p0 * ldf, ldf, np, B, rows_b, nullptr, st)) return rc;
-    if (int rc = gi_run(ctx, s, s->a, slabs, 0, s->b, slabs, slabs, false, FP, B, R, ldr, st)) return rc;
+    float* Fc = const_cast<float*>(F) + p0 * ldf;
+    if (int rc = gi_split<true>(DH + p0 * lda, lda, np, FP, GI_ROWS, x->scale, s->a_data, nullptr, st)) return rc;
+    if (int rc = xop_colmax(ctx, Fc, ldf, np, B, b_cmax, st)) return rc;
+    if (int rc = xop_exps(b_cmax, B, rows_b, 0, b_exps, b_scale, nullptr, st)) return rc;
+    if (int rc = gi_split<false>(Fc, ldf, np, B, rows_b, b_scale, s->b_data, nullptr, st)) return rc;
+    if (int rc = gi_run(ctx, s, pa, slabs, 0, pb, slabs, slabs, false, FP, B, R, ldr, st)) return rc;
   }
   return 0;
+}
+
+// size the context-owned buffers of the projection for n rows and B right-hand sides (fps_reserve_workspace)
+int gram_i8_reserve(fps_ctx* ctx, int64_t n, int B) {
+  GiState* s;
+  if (int rc = gi_state_get(ctx, &s)) return rc;
+  const int pairs = ctx->sm_count / 2;
+  int st_, sp_;
+  int nitems = gi_nitems(GI_NTILES, (n + GI_SLAB - 1) / GI_SLAB, pairs, 128, &st_, &sp_);
+  if (B > 0) {
+    const int rows_b = (B + 63) / 64 * 64;
+    const int64_t chunk = gi_project_chunk(rows_b, n, GI_MAX_CHUNK);
+    if (int rc = gi_reserve_b(ctx, s, rows_b, chunk)) return rc;
+    nitems = std::max(nitems, gi_nitems(3 * (rows_b / 64), (chunk + GI_SLAB - 1) / GI_SLAB, pairs, 128, &st_, &sp_));
+  }
+  return gi_reserve_partial(ctx, s, nitems);
 }
 
 }  // namespace fps

@@ -108,6 +108,13 @@ struct TcParams {
   float* H;
   float* DH;
   unsigned* dh_cmax;  // per-feature max |DH| (float bits, atomicMax), feeds the exact int8 Gram; may be null
+  // exact-engine outputs of the last layer (struct FusedOut): DH snapped to the calibrated grid dh_scale and written as
+  // point-major digit planes (gram_i8.cu layout) for the points [point0, ...); dh_flag is raised on overflow
+  int8_t* gplanes;
+  const float2* dh_scale;
+  int* dh_flag;
+  int64_t point0;
+  int snap_h;         // snap H to the uniform 2^-30 grid
   int64_t ld;
   int64_t rows;   // valid activation rows = points * S
   int nk;         // K slabs of TK
@@ -368,27 +375,76 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
       // entirely inside the wave (all but the last row tile) skip the test
       const bool tile_full = r0 + TN / 2 <= P.rows;
       const size_t o0 = (size_t)r0 * FP + f;   // element offset of (row r0, feature f) in the output planes
-      if (f_ok) {
+      if (S == 4 && LAST) {
+        // H, DH and (fused with the exact int8 engine, gram_i8.cu) the digit planes of DH.  This thread owns feature f
+        // of 32 consecutive points: per digit that is one 32-byte run of planes[slab][digit][f][point % 128].  Lanes with
+        // f in [704, 768) are tile padding but still own (all-zero) plane rows.
+        const bool planes = P.gplanes != nullptr;
+        const float2 sd = (planes && f_ok) ? P.dh_scale[f] : make_float2(0.f, 0.f);
+        uint32_t dg[4][8];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) dg[s4][w8] = 0u;
+        float dh_max = 0.f;
+        bool ovf = false;
+#pragma unroll
+        for (int q = 0; q < TN / 8; ++q) {
+          float o[4];
+          tanh_streams(fmaf(acc[4 * q], P.in_inv[0], bias), acc[4 * q + 1] * P.in_inv[1],
+                       acc[4 * q + 2] * P.in_inv[2], acc[4 * q + 3] * P.in_inv[3], o[0], o[1], o[2], o[3]);
+          const bool valid = tile_full || r0 + q * 4 < P.rows;
+          float hv = o[0], dv = o[3];
+          if (P.snap_h) hv = (float)__float2int_rn(hv * 1073741824.0f) * 9.313225746154785e-10f;   // |h| <= 1: exact
+          if (planes) {
+            const float t = dv * sd.x;                       // sd.x = 2^(30 - e_f): exact
+            int X = 0;
+            if (fabsf(t) <= 1073741824.0f) {
+              X = __float2int_rn(t);
+              dv = (float)X * sd.y;                          // exact: X has at most 24 significant bits
+            } else if (valid) {
+              ovf = true;                                    // beyond the calibrated grid: keep dv, redo the split later
+            }
+            if (!valid) X = 0;
+#pragma unroll
+            for (int s4 = 3; s4 >= 1; --s4) {
+              const int d = ((X + 128) & 255) - 128;         // balanced digit in [-128, 127]
+              X = (X - d) >> 8;
+              dg[s4][q >> 2] |= (uint32_t)(d & 255) << (8 * (q & 3));
+            }
+            dg[0][q >> 2] |= (uint32_t)(X & 255) << (8 * (q & 3));
+          }
+          if (valid && f_ok) {
+            const int64_t p = (r0 >> 2) + q;
+            P.H[p * P.ld + f] = hv;
+            P.DH[p * P.ld + f] = dv;
+            dh_max = fmaxf(dh_max, fabsf(o[3]));
+          }
+        }
+        if (f_ok && P.dh_cmax) atomicMax(P.dh_cmax + f, __float_as_uint(dh_max));
+        if (ovf) *P.dh_flag = 1;
+        if (planes) {
+          const int64_t pg = P.point0 + (r0 >> 2);           // first of this thread's 32 points (a multiple of 32)
+          int8_t* base = P.gplanes + (((pg >> 7) * 4) * FPW + f) * 128 + (pg & 127);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            uint4* dst = reinterpret_cast<uint4*>(base + (int64_t)s4 * FPW * 128);
+            dst[0] = make_uint4(dg[s4][0], dg[s4][1], dg[s4][2], dg[s4][3]);
+            dst[1] = make_uint4(dg[s4][4], dg[s4][5], dg[s4][6], dg[s4][7]);
+          }
+        }
+      } else if (f_ok) {
         if (S == 4) {
-          float dh_max = 0.f;
 #pragma unroll
           for (int q = 0; q < TN / 8; ++q) {
             float o[4];
             tanh_streams(fmaf(acc[4 * q], P.in_inv[0], bias), acc[4 * q + 1] * P.in_inv[1],
                          acc[4 * q + 2] * P.in_inv[2], acc[4 * q + 3] * P.in_inv[3], o[0], o[1], o[2], o[3]);
             if (tile_full || r0 + q * 4 < P.rows) {
-              if (LAST) {
-                const int64_t p = (r0 >> 2) + q;
-                P.H[p * P.ld + f] = o[0];
-                P.DH[p * P.ld + f] = o[3];
-                dh_max = fmaxf(dh_max, fabsf(o[3]));
-              } else {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) store_planes_t<F16>(P.out, o0 + (size_t)(q * 4 + s) * FP, o[s], P.out_sc[s]);
-              }
+              for (int s = 0; s < 4; ++s) store_planes_t<F16>(P.out, o0 + (size_t)(q * 4 + s) * FP, o[s], P.out_sc[s]);
             }
           }
-          if (LAST && P.dh_cmax) atomicMax(P.dh_cmax + f, __float_as_uint(dh_max));
         } else {
 #pragma unroll
           for (int q = 0; q < TN / 2; ++q) {
@@ -550,7 +606,7 @@ static float kappa_of(int kseg, bool f16) {
 }
 
 int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int64_t points, int streams, bool last,
-                    float* H, float* DH, int64_t ld, cudaStream_t st) {
+                    float* H, float* DH, int64_t ld, const FusedOut* fused, cudaStream_t st) {
   if (points <= 0) return 0;
   const TcState* s = static_cast<const TcState*>(ctx->tc_state);
   FPS_REQUIRE(s, "tcgen05 engine not initialised");
@@ -564,7 +620,15 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.out = out;
   P.H = H;
   P.DH = DH;
-  P.dh_cmax = (last && DH) ? ctx->dh_cmax : nullptr;
+  const bool fz = last && DH && fused && fused->xdh;
+  P.dh_cmax = fz ? fused->xdh->cmax : nullptr;
+  P.gplanes = fz ? fused->gplanes : nullptr;
+  P.dh_scale = fz ? fused->xdh->scale : nullptr;
+  P.dh_flag = fz ? fused->xdh->flags : nullptr;
+  P.point0 = fz ? fused->point0 : 0;
+  P.snap_h = (last && DH && fused) ? fused->snap_h : 0;
+  FPS_REQUIRE(!P.gplanes || (P.point0 % 128 == 0 && (uintptr_t)P.gplanes % 16 == 0),
+              "layer_tc: fused digit planes need a 128-point aligned wave and a 16-byte aligned buffer");
   P.sched = ctx->tc_sched;
   P.ld = ld;
   P.rows = points * streams;
@@ -591,6 +655,7 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   const int tail = (P.nk % seg) ? (P.nk % seg) : seg;
   P.gain = 1.0f + (kenv ? (float)atof(kenv) : kappa_of(seg * slab_k, f16));
   P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail * slab_k, f16));
+  if (ctx->gain_off) P.gain = P.gain_tail = 1.0f;   // fps_calibrate_scales found the compensation harmful for these weights
   const int ncta = s->pair ? 2 : 1;
   {
     const int stage_bytes = (wide ? 128 : 64) * BOX_ROWS * (2 + 2 * (TN / BOX_ROWS / ncta));

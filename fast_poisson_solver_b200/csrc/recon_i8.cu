@@ -263,6 +263,9 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       mbar_wait(bar_tfull, tphase);
       tphase ^= 1;
       tc_fence_after();
+      // Phase 1 (TMEM-read bound): pull the five orders out and fold them into one 64-bit integer per output, then hand
+      // the accumulators back to the MMA issuer at once; phase 2 (conversion, scaling, stores) overlaps the next tile.
+      long long S[RI_TN / 2];
 #pragma unroll
       for (int c = 0; c < RI_TN / 32; ++c) {
         int v[RI_NORD][16];
@@ -271,16 +274,20 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          long long S = v[0][q];
+          long long acc = v[0][q];
 #pragma unroll
-          for (int o = 1; o < RI_NORD; ++o) S = S * 256 + v[o][q];
-          const int64_t i = i0 + c * 16 + q;
-          if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)fma((double)S, scale, bj);
+          for (int o = 1; o < RI_NORD; ++o) acc = acc * 256 + v[o][q];
+          S[c * 16 + q] = acc;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_tempty);
+#pragma unroll
+      for (int q = 0; q < RI_TN / 2; ++q) {
+        const int64_t i = i0 + q;
+        if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)fma((double)S[q], scale, bj);
+      }
     }
   }
 
@@ -294,46 +301,11 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 }
 
 // ---- host -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ri_colmax_kernel(const float* __restrict__ A, int64_t ld, int64_t n, int64_t rows_per_cta, unsigned* __restrict__ cmax) {
-  const int t = threadIdx.x;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
-  const bool has2 = t + 512 < FP;
-  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    const float* row = A + r * ld;
-    m0 = fmaxf(m0, fabsf(__ldg(row + t)));
-    m1 = fmaxf(m1, fabsf(__ldg(row + t + 256)));
-    if (has2) m2 = fmaxf(m2, fabsf(__ldg(row + t + 512)));
-  }
-  atomicMax(cmax + t, __float_as_uint(m0));
-  atomicMax(cmax + t + 256, __float_as_uint(m1));
-  if (has2) atomicMax(cmax + t + 512, __float_as_uint(m2));
-}
-
-// same exponent / scale rule as gram_i8.cu (the grids must agree so that a snapped DH stays put)
-__global__ void ri_exps_kernel(const unsigned* __restrict__ cmax, int* __restrict__ exps, float2* __restrict__ scale) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= FPW) return;
-  int e = 0;
-  if (f < FP) {
-    const unsigned bits = cmax[f];
-    const int E = (int)(bits >> 23);
-    e = bits ? ((E > 0 ? E : 1) - 126) : 0;
-    if (e < -90) e = -90;
-  }
-  exps[f] = e;
-  scale[f] = make_float2(ldexpf(1.0f, 30 - e), ldexpf(1.0f, e - 30));
-}
-
 struct RiState {
-  int8_t* pa = nullptr;      // digit planes of A: RI_DA x n_pad x FP
+  int8_t* pa = nullptr;      // context-owned digit planes of A (uncached entry point): RI_DA x n_pad x FP
   size_t pa_bytes = 0;
   int8_t* pw = nullptr;      // digit planes of W': RI_DW x b_pad x FP
   size_t pw_bytes = 0;
-  unsigned* cmax = nullptr;  // FPW x {cmax, exps, scale}
-  int* exps = nullptr;
-  float2* scale = nullptr;
   int* gw = nullptr;         // b_pad exponents
   int gw_cap = 0;
   void* encode = nullptr;
@@ -348,10 +320,23 @@ void recon_i8_destroy(fps_ctx* ctx) {
   if (!s) return;
   cudaFree(s->pa);
   cudaFree(s->pw);
-  cudaFree(s->cmax);
   cudaFree(s->gw);
   delete s;
   ctx->ri_state = nullptr;
+}
+
+static int ri_state_get(fps_ctx* ctx, RiState** out) {
+  RiState* s = static_cast<RiState*>(ctx->ri_state);
+  if (!s) {
+    s = new RiState();
+    ctx->ri_state = s;
+    cudaDriverEntryPointQueryResult qres;
+    FPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &s->encode, cudaEnableDefault, &qres));
+    FPS_REQUIRE(s->encode && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    FPS_CUDA(cudaFuncSetAttribute(recon_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RI_SMEM));
+  }
+  *out = s;
+  return 0;
 }
 
 static int ri_map(RiState* s, CUtensorMap* m, const int8_t* base, int64_t rows, int box_rows) {
@@ -366,34 +351,12 @@ static int ri_map(RiState* s, CUtensorMap* m, const int8_t* base, int64_t rows, 
   return 0;
 }
 
-constexpr int64_t RI_MAX_CHUNK = 1 << 20;   // points per pass: 2.75 GiB of digit planes
+constexpr int64_t RI_MAX_CHUNK = 1 << 20;   // points per pass through context-owned planes: 2.75 GiB
 
-// out (n x B, ldo) = A W + bias;  A (n x >= FP, lda) is snapped in place (see the header)
-int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double* W, int64_t ldw, const double* bias,
-                    int B, float* out, int64_t ldo, cudaStream_t st) {
-  if (n <= 0 || B <= 0) return 0;
-  RiState* s = static_cast<RiState*>(ctx->ri_state);
-  if (!s) {
-    s = new RiState();
-    ctx->ri_state = s;
-    cudaDriverEntryPointQueryResult qres;
-    FPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &s->encode, cudaEnableDefault, &qres));
-    FPS_REQUIRE(s->encode && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
-    FPS_CUDA(cudaMalloc(&s->cmax, FPW * (sizeof(unsigned) + sizeof(int) + sizeof(float2))));
-    s->exps = reinterpret_cast<int*>(s->cmax + FPW);
-    s->scale = reinterpret_cast<float2*>(s->cmax + 2 * FPW);
-    FPS_CUDA(cudaFuncSetAttribute(recon_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RI_SMEM));
-  }
-  const int b_pad = (B + 2 * RI_TM - 1) / (2 * RI_TM) * (2 * RI_TM);
-  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : RI_MAX_CHUNK;
-  const int64_t chunk = n < max_chunk ? n : max_chunk;
-  const int64_t cap_pad = (chunk + RI_TN - 1) / RI_TN * RI_TN;
-  if ((size_t)RI_DA * cap_pad * FP > s->pa_bytes) {
-    if (s->pa) { FPS_CUDA(cudaFree(s->pa)); ctx->workspace_bytes -= s->pa_bytes; s->pa = nullptr; s->pa_bytes = 0; }
-    FPS_CUDA(cudaMalloc(&s->pa, (size_t)RI_DA * cap_pad * FP));
-    s->pa_bytes = (size_t)RI_DA * cap_pad * FP;
-    ctx->workspace_bytes += s->pa_bytes;
-  }
+static int64_t ri_pad(int64_t n) { return (n + RI_TN - 1) / RI_TN * RI_TN; }
+size_t recon_planes_bytes(int64_t n) { return n > 0 ? (size_t)RI_DA * ri_pad(n) * FP : 0; }
+
+static int ri_reserve_w(fps_ctx* ctx, RiState* s, int b_pad) {
   if ((size_t)RI_DW * b_pad * FP > s->pw_bytes) {
     if (s->pw) { FPS_CUDA(cudaFree(s->pw)); ctx->workspace_bytes -= s->pw_bytes; s->pw = nullptr; s->pw_bytes = 0; }
     FPS_CUDA(cudaMalloc(&s->pw, (size_t)RI_DW * b_pad * FP));
@@ -405,47 +368,108 @@ int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double
     FPS_CUDA(cudaMalloc(&s->gw, (size_t)b_pad * sizeof(int)));
     s->gw_cap = b_pad;
   }
-  const bool have_cmax = ctx->dh_cmax_of == A && ctx->dh_cmax_n == n;
+  return 0;
+}
+
+int recon_i8_reserve(fps_ctx* ctx, int B) {
+  RiState* s;
+  if (int rc = ri_state_get(ctx, &s)) return rc;
+  if (B <= 0) return 0;
+  return ri_reserve_w(ctx, s, (B + 2 * RI_TM - 1) / (2 * RI_TM) * (2 * RI_TM));
+}
+
+// digit planes of np rows of A on the grid of x (written to `planes` = RI_DA x ri_pad(np) x FP); A is snapped in place
+// (nothing is written for an A that already lies on the grid)
+static int ri_split_a(float* A, int64_t lda, int64_t np, const Xop* x, int8_t* planes, cudaStream_t st) {
+  const int64_t n_pad = ri_pad(np);
+  const int64_t threads = n_pad * (FP / 4);
+  ri_split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(A, lda, np, n_pad, x->scale, planes);
+  count_launch();
+  FPS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out (np x B, ldo) = X W + bias from digit planes of np rows
+static int ri_run(fps_ctx* ctx, RiState* s, const Xop* x, const int8_t* planes, int64_t np, const double* W, int64_t ldw,
+                  const double* bias, int B, float* out, int64_t ldo, cudaStream_t st) {
+  const int b_pad = (B + 2 * RI_TM - 1) / (2 * RI_TM) * (2 * RI_TM);
+  if (int rc = ri_reserve_w(ctx, s, b_pad)) return rc;
+  const int64_t n_pad = ri_pad(np);
+  FPS_REQUIRE((int64_t)RI_DA * n_pad < ((int64_t)1 << 31), "recon_i8: %lld points exceed the 32-bit tile coordinates",
+              (long long)np);
+  ri_wexp_kernel<<<(b_pad + 31) / 32, 256, 0, st>>>(W, ldw, B, b_pad, x->exps, s->gw);
+  ri_split_w_kernel<<<dim3((b_pad + 255) / 256, FP / 4), 256, 0, st>>>(W, ldw, B, b_pad, x->exps, s->gw, s->pw);
+  FPS_CUDA(cudaGetLastError());
+  CUtensorMap tmW, tmA;
+  if (ri_map(s, &tmW, s->pw, (int64_t)RI_DW * b_pad, RI_TM)) return 2;
+  if (ri_map(s, &tmA, planes, (int64_t)RI_DA * n_pad, RI_TN)) return 2;
+  RiParams P;
+  P.out = out;
+  P.ldo = ldo;
+  P.n = np;
+  P.B = B;
+  P.gw = s->gw;
+  P.bias = bias;
+  P.rhs_blocks = b_pad / (2 * RI_TM);
+  P.point_blocks = (int)(n_pad / RI_TN);
+  P.n_pad = (int)n_pad;
+  P.b_pad = b_pad;
+  const int pairs = ctx->sm_count / 2;
+  const int64_t ntiles = (int64_t)P.rhs_blocks * P.point_blocks;
+  FPS_REQUIRE(ntiles < ((int64_t)1 << 31), "recon_i8: too many tiles");
+  const int groups = (int)std::min<int64_t>(ntiles, pairs);
+  recon_i8_kernel<<<groups * 2, RI_THREADS, RI_SMEM, st>>>(tmW, tmA, P);
+  FPS_CUDA(cudaGetLastError());
+  count_launch(3);
+  return 0;
+}
+
+// ---- cached form: the caller owns the descriptor and the planes of all n rows -------------------------------------------
+// need_grid: derive the grid of x from the column maxima of A first (false: x already holds it, e.g. from the feature
+// kernel or from the Gram of the same matrix)
+int launch_recon_planes_build(fps_ctx* ctx, float* A, int64_t lda, int64_t n, Xop* x, int8_t* planes, bool need_grid,
+                              cudaStream_t st) {
+  if (n <= 0) return 0;
+  RiState* s;
+  if (int rc = ri_state_get(ctx, &s)) return rc;
+  if (need_grid) {
+    if (int rc = xop_colmax(ctx, A, lda, n, FP, x->cmax, st)) return rc;
+    if (int rc = xop_exps(x->cmax, FP, XOP_ROWS, 0, x->exps, x->scale, nullptr, st)) return rc;
+  }
+  return ri_split_a(A, lda, n, x, planes, st);
+}
+
+int launch_recon_x(fps_ctx* ctx, const Xop* x, const int8_t* planes, int64_t n, const double* W, int64_t ldw,
+                   const double* bias, int B, float* out, int64_t ldo, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  RiState* s;
+  if (int rc = ri_state_get(ctx, &s)) return rc;
+  return ri_run(ctx, s, x, planes, n, W, ldw, bias, B, out, ldo, st);
+}
+
+// ---- uncached form (fps_reconstruct on any matrix): planes in the context workspace, passes of <= 2^20 points, one grid
+// for all n rows; A is snapped in place (see the header) ------------------------------------------------------------------
+int launch_recon_i8(fps_ctx* ctx, float* A, int64_t lda, int64_t n, const double* W, int64_t ldw, const double* bias,
+                    int B, float* out, int64_t ldo, cudaStream_t st) {
+  if (n <= 0 || B <= 0) return 0;
+  RiState* s;
+  if (int rc = ri_state_get(ctx, &s)) return rc;
+  static const int64_t max_chunk = getenv("FPS_GRAM_I8_CHUNK") ? atoll(getenv("FPS_GRAM_I8_CHUNK")) : RI_MAX_CHUNK;
+  const int64_t chunk = n < max_chunk ? n : max_chunk;
+  const size_t need = recon_planes_bytes(chunk);
+  if (need > s->pa_bytes) {
+    if (s->pa) { FPS_CUDA(cudaFree(s->pa)); ctx->workspace_bytes -= s->pa_bytes; s->pa = nullptr; s->pa_bytes = 0; }
+    FPS_CUDA(cudaMalloc(&s->pa, need));
+    s->pa_bytes = need;
+    ctx->workspace_bytes += need;
+  }
+  Xop* x = ctx->xop_tmp;
+  if (int rc = xop_colmax(ctx, A, lda, n, FP, x->cmax, st)) return rc;
+  if (int rc = xop_exps(x->cmax, FP, XOP_ROWS, 0, x->exps, x->scale, nullptr, st)) return rc;
   for (int64_t p0 = 0; p0 < n; p0 += chunk) {
     const int64_t np = (n - p0 < chunk) ? n - p0 : chunk;
-    const int64_t n_pad = (np + RI_TN - 1) / RI_TN * RI_TN;
-    float* Ac = A + p0 * lda;
-    if (!have_cmax) {
-      FPS_CUDA(cudaMemsetAsync(s->cmax, 0, FPW * sizeof(unsigned), st));
-      int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (np + 31) / 32);
-      const int64_t rpc = (np + ctas - 1) / ctas;
-      ctas = (np + rpc - 1) / rpc;
-      ri_colmax_kernel<<<(unsigned)ctas, 256, 0, st>>>(Ac, lda, np, rpc, s->cmax);
-      count_launch(1);
-    }
-    ri_exps_kernel<<<(FPW + 255) / 256, 256, 0, st>>>(have_cmax ? ctx->dh_cmax : s->cmax, s->exps, s->scale);
-    {
-      const int64_t threads = n_pad * (FP / 4);
-      ri_split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Ac, lda, np, n_pad, s->scale, s->pa);
-    }
-    ri_wexp_kernel<<<(b_pad + 31) / 32, 256, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw);
-    ri_split_w_kernel<<<dim3((b_pad + 255) / 256, FP / 4), 256, 0, st>>>(W, ldw, B, b_pad, s->exps, s->gw, s->pw);
-    FPS_CUDA(cudaGetLastError());
-    CUtensorMap tmW, tmA;
-    if (ri_map(s, &tmW, s->pw, (int64_t)RI_DW * b_pad, RI_TM)) return 2;
-    if (ri_map(s, &tmA, s->pa, (int64_t)RI_DA * n_pad, RI_TN)) return 2;
-    RiParams P;
-    P.out = out + p0 * ldo;
-    P.ldo = ldo;
-    P.n = np;
-    P.B = B;
-    P.gw = s->gw;
-    P.bias = bias;
-    P.rhs_blocks = b_pad / (2 * RI_TM);
-    P.point_blocks = (int)(n_pad / RI_TN);
-    P.n_pad = (int)n_pad;
-    P.b_pad = b_pad;
-    const int pairs = ctx->sm_count / 2;
-    const int64_t ntiles = (int64_t)P.rhs_blocks * P.point_blocks;
-    const int groups = (int)std::min<int64_t>(ntiles, pairs);
-    recon_i8_kernel<<<groups * 2, RI_THREADS, RI_SMEM, st>>>(tmW, tmA, P);
-    FPS_CUDA(cudaGetLastError());
-    count_launch(5);
+    if (int rc = ri_split_a(A + p0 * lda, lda, np, x, s->pa, st)) return rc;
+    if (int rc = ri_run(ctx, s, x, s->pa, np, W, ldw, bias, B, out + p0 * ldo, ldo, st)) return rc;
   }
   return 0;
 }

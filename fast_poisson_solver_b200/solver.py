@@ -23,16 +23,18 @@ Deliberate deviations from the reference:
     reconstruction are fp64 grade - exact integer arithmetic on the int8 tensor cores for N >= 16384 points
     (and >= 32 right-hand sides), fp64 accumulation otherwise - and the factorisation is fp64.
     precision=torch.float64: everything, including the feature network, runs in fp64 (DMMA).
-  * For N >= 16384 the stored ``DH`` (and ``H`` once a batched solve has used it) is snapped to a 31-bit
-    fixed-point grid per feature column: elements below 2^-7 of the column maximum move by less than 2^-31 of
-    it (under 1 % of one fp32 ulp of the maximum), all others are unchanged.  The Gram matrix is then the exact
-    Gram of the stored ``DH`` (csrc/gram_i8.cu).
+  * For N >= 16384 (float32 mode) ``precompute`` stores ``H`` and ``DH`` on fixed-point grids: ``H`` on multiples of
+    2^-30 (|H| <= 1), ``DH`` on a 31-bit grid per feature column (elements far below the column maximum move by
+    2^-31..2^-29 of it, under 1 % of one fp32 ulp of the maximum; all others are unchanged).  The Gram matrix is the exact
+    Gram of the stored ``DH`` (csrc/gram_i8.cu).  ``solve`` never modifies precomputed state.
   * ``distributed=True``: every rank passes ITS shard of the collocation / boundary points and of
     the rows of ``f``; one all-reduce of the packed [Gram | BC Gram | column sums | counts] buffer
     in precompute and one of the projected right-hand sides per solve.
 """
 from __future__ import annotations
 
+import ctypes as C
+import hashlib
 import os
 import pickle
 import random
@@ -46,6 +48,8 @@ from .parallel import PackedNormal, allreduce_sum
 
 F, FP = _lib.F, _lib.FP
 _JITTER_LADDER = [0.0, 8.0, 128.0, 2048.0, 32768.0, 2.0 ** 20, 2.0 ** 26, 2.0 ** 32]  # x eps x max_diag
+_FORMAT = "fps_b200/3"
+_MIN_B_EXACT = 32   # right-hand sides from which projection / reconstruction use the int8 engine
 
 
 def format_input(v, precision=torch.float32, device="cpu", as_array=False, reshape=True):
@@ -81,7 +85,7 @@ def _as_f64_column(item, device):
 class Solver:
     def __init__(self, device="cuda", precision=torch.float32, verbose=False, use_weights=True, compile_model=True,
                  lambdas_pde=None, seed=0, *, weights=None, engine=None, chunk_points=0, distributed=False,
-                 process_group=None):
+                 process_group=None, cache_planes=None):
         if not torch.cuda.is_available():
             raise RuntimeError(
                 "fast_poisson_solver_b200.Solver needs a CUDA device (B200 / sm_100a); there is no CPU fallback. "
@@ -136,12 +140,12 @@ class Solver:
         else:
             sd = _weights.default_init(seed)
         self._host_weights = _weights.HostWeights(sd)
+        self.weights_sha256 = self._host_weights.sha256()
 
         self._lib = _lib.load()
         if engine is None:
             engine = os.environ.get("FPS_ENGINE", "tcgen05")
         self.engine = {"simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05}[engine] if isinstance(engine, str) else int(engine)
-        import ctypes as C
 
         self._ctx = C.c_void_p()
         with torch.cuda.device(self._dev_index):
@@ -149,8 +153,14 @@ class Solver:
                                             int(chunk_points), self.engine), "fps_create")
         self._ready = False
         # precision=float64 runs the full-fp64 feature engine (DMMA) and keeps H / DH / outputs in fp64;
-        # precision=float32 runs the 3xTF32 tcgen05 engine with fp32 features and fp64 normal equations.
+        # precision=float32 runs the tcgen05 engine with fp32-grade features and fp64-grade normal equations.
         self._fdtype = torch.float64 if precision == torch.float64 else torch.float32
+        # digit planes of the exact int8 engine are kept between calls when memory allows (None = decide per problem:
+        # at most a quarter of the free device memory; FPS_CACHE_PLANES=0/1 or cache_planes=False/True force it)
+        env = os.environ.get("FPS_CACHE_PLANES")
+        self._cache_planes = cache_planes if cache_planes is not None else (None if env is None else env != "0")
+        self._exact_min = int(self._lib.fps_exact_min_rows())
+        self._reserved = (0, 0)
 
     def _fn(self, name):
         return getattr(self._lib, name + ("_f64" if self._fdtype == torch.float64 else ""))
@@ -159,7 +169,7 @@ class Solver:
     def __del__(self):
         try:
             if getattr(self, "_ctx", None) and self._ctx.value:
-                self._lib.fps_destroy(self._ctx)
+                self._lib.fps_destroy(self._ctx)   # restores the caller's current device itself
                 self._ctx.value = None
         except Exception:
             pass
@@ -182,38 +192,70 @@ class Solver:
                        "fps_features")
         return H, DH
 
+    def _exact(self, n):
+        """True when n rows go through the cached exact int8 engine (float32 mode, n >= fps_exact_min_rows())."""
+        return self._fdtype == torch.float32 and n >= self._exact_min
+
+    def _want_cache(self, nbytes):
+        if self._cache_planes is not None:
+            return bool(self._cache_planes)
+        free, _ = torch.cuda.mem_get_info(self._dev_index)
+        free += torch.cuda.memory_reserved(self._dev_index) - torch.cuda.memory_allocated(self._dev_index)
+        return nbytes <= free // 4
+
+    def _alloc_planes(self, nbytes):
+        try:
+            return torch.empty(nbytes, dtype=torch.int8, device=self._tdev)
+        except torch.cuda.OutOfMemoryError:
+            return None
+
+    def _reserve(self, n, B):
+        """Size the library's own scratch for (n rows, B right-hand sides) so that no call allocates mid-stream."""
+        if self._exact(n) and (n > self._reserved[0] or B > self._reserved[1]):
+            self._reserved = (max(n, self._reserved[0]), max(B, self._reserved[1]))
+            _lib.check(self._lib.fps_reserve_workspace(self._ctx, self._reserved[0], self._reserved[1]),
+                       "fps_reserve_workspace")
+
     def _allreduce(self, t):
         allreduce_sum(t, self.process_group)
 
-    def _factor(self):
-        """Assemble LHS per lambda and Cholesky-factor it (fps_assemble_factor), raising the diagonal
-        shift only if the factorisation reports a non-positive pivot."""
-        import ctypes as C
-
+    def _enqueue_factor(self, jitter):
         nl = self.n_lambdas
         lam = (C.c_double * nl)(*[float(l) for l in self.lambdas_pde])
+        jit = (C.c_double * nl)(*jitter)
+        _lib.check(self._lib.fps_assemble_factor_packed(self._ctx, self._pack.data_ptr(), lam, jit, nl,
+                                                        self._L64.data_ptr(), self._info.data_ptr(), self._stream()),
+                   "fps_assemble_factor_packed")
+
+    def _factor(self):
+        """Assemble LHS per lambda and Cholesky-factor it (solver.py:187-199 + the LU of :305).  The first attempt is
+        enqueued without any host round trip; `_finish_factor` looks at the pivot report once the stream is drained."""
+        nl = self.n_lambdas
         self._L64 = torch.empty((nl, _lib.LROWS, FP), dtype=torch.float64, device=self._tdev)
-        info = torch.zeros(nl, dtype=torch.int32, device=self._tdev)
+        self._info = torch.zeros(nl, dtype=torch.int32, device=self._tdev)
+        self.jitter = [0.0] * nl
+        self._enqueue_factor(self.jitter)
+
+    def _finish_factor(self):
+        """Raise the diagonal shift only if the factorisation reported a non-positive pivot (rank-deficient systems,
+        e.g. fewer equations than features).  Slow path: host-driven ladder."""
+        nl = self.n_lambdas
+        bad = self._info.cpu().numpy()
+        if not bad.any():
+            return
         diag_scale = [float(l) / self.NO * float(self._G64.diagonal()[:F].max()) +
                       float(self._Gbc64.diagonal()[:F].max()) / self.NdO for l in self.lambdas_pde]
         level = [0] * nl
-        self.jitter = [0.0] * nl
-        for _ in range(len(_JITTER_LADDER)):
-            jit = (C.c_double * nl)(*self.jitter)
-            _lib.check(self._lib.fps_assemble_factor(self._ctx, self._G64.data_ptr(), self._Gbc64.data_ptr(),
-                                                     self._s64.data_ptr(), self.NO, self.NdO, lam, jit, nl,
-                                                     self._L64.data_ptr(), info.data_ptr(), self._stream()),
-                       "fps_assemble_factor")
-            bad = info.cpu().numpy()
-            if not bad.any():
-                break
+        while bad.any():
             for i in range(nl):
                 if bad[i]:
                     level[i] += 1
                     if level[i] >= len(_JITTER_LADDER):
                         raise _lib.FpsError("normal matrix could not be factored even with the largest diagonal shift")
                     self.jitter[i] = _JITTER_LADDER[level[i]] * np.finfo(np.float64).eps * diag_scale[i]
-        if self.verbose > 0 and any(self.jitter):
+            self._enqueue_factor(self.jitter)
+            bad = self._info.cpu().numpy()
+        if self.verbose > 0:
             print("Cholesky needed a diagonal shift:", self.jitter)
 
     # ---- reference API -----------------------------------------------------------------------------
@@ -232,17 +274,17 @@ class Solver:
             self.x_pde, self.y_pde, self.x_bc, self.y_bc = [t.to(self.precision).reshape(-1, 1) for t in x64]
             self.x_tot = torch.cat([self.x_pde, self.x_bc], dim=0)
             self.y_tot = torch.cat([self.y_pde, self.y_bc], dim=0)
+            # range check of solver.py:244-247: evaluated on the device now, read back (and raised) at the end of
+            # precompute, where the stream is drained anyway - no host round trip in the middle of the pipeline
+            rng = None
             if self.x_tot.numel():
-                assert torch.min(self.x_tot) >= 0 and torch.max(self.x_tot) <= 1, \
-                    "x coordinates should be in [0, 1]. Please rescale."
-                assert torch.min(self.y_tot) >= 0 and torch.max(self.y_tot) <= 1, \
-                    "y coordinates should be in [0, 1]. Please rescale."
+                rng = torch.stack(torch.aminmax(self.x_tot) + torch.aminmax(self.y_tot)).double()
 
             # drop the previous domain's feature matrices first: at 16M points they are 47 GB each
-            for name in ("H", "DH", "Dht", "H_bc", "Ht_bc", "_Hp", "_DHp", "_Hbcp", "u_pred", "u_pde_pred", "u_bc_pred",
-                         "f_pred", "f", "bc"):
-                if hasattr(self, name):
-                    setattr(self, name, None)
+            for attr in ("H", "DH", "Dht", "H_bc", "Ht_bc", "_Hp", "_DHp", "_Hbcp", "u_pred", "u_pde_pred", "u_bc_pred",
+                         "f_pred", "f", "bc", "_gplanes", "_rplanes_h", "_rplanes_dh", "_W64", "_bias64"):
+                if hasattr(self, attr):
+                    setattr(self, attr, None)
             use_file = bool(load) and os.path.isfile(self.precompute_file)
             if self.distributed and load:
                 # every rank must take the same branch (the recompute branch contains collectives)
@@ -251,54 +293,107 @@ class Solver:
                 flag = torch.tensor([1.0 if use_file else 0.0], device=self._tdev)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.process_group)
                 use_file = flag.item() > 0.5
+            loaded = False
             if use_file:
-                self._load_precomputed()
-            else:
-                if self._fdtype == torch.float32 and x64[0].numel():
-                    # fit the fp16 operand scales of the tensor-core engine to this network / domain (1 ms)
-                    # on an evenly strided sample of the collocation points (grids come sorted)
-                    n_all = x64[0].numel()
-                    if n_all > 512:
-                        pick = torch.linspace(0, n_all - 1, 512, device=self._tdev).long()
-                        xs, ys = x64[0][pick].contiguous(), x64[1][pick].contiguous()
-                    else:
-                        xs, ys = x64[0], x64[1]
-                    _lib.check(self._lib.fps_calibrate_scales(self._ctx, xs.data_ptr(), ys.data_ptr(), xs.numel(),
-                                                              self._stream()), "fps_calibrate_scales")
-                self._Hp, self._DHp = self._features(x64[0], x64[1], True)      # solver.py:162-166
-                self._Hbcp, _ = self._features(x64[2], x64[3], False)           # solver.py:173-175
-                packed = PackedNormal(self._tdev)
-                pack = packed.buf
-                self._G64, self._Gbc64, self._s64 = packed.G, packed.Gbc, packed.s
-                st = self._stream()
-                n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
-                if n_loc:
-                    _lib.check(self._fn("fps_gram_accum")(self._ctx, self._DHp.data_ptr(), n_loc, FP,
-                                                        self._G64.data_ptr(), st), "fps_gram_accum")  # solver.py:167
-                if nbc_loc:
-                    _lib.check(self._fn("fps_gram_accum")(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
-                                                        self._Gbc64.data_ptr(), st), "fps_gram_accum(bc)")
-                    _lib.check(self._fn("fps_colsum_accum")(self._ctx, self._Hbcp.data_ptr(), nbc_loc, FP,
-                                                          self._s64.data_ptr(), st), "fps_colsum_accum")  # solver.py:176-178
-                packed.set_counts(n_loc, nbc_loc)
+                loaded = self._load_precomputed(x64[0].numel(), x64[2].numel())
                 if self.distributed:
-                    packed.allreduce(self.process_group)  # the path's one exchange step
-                    self.NO, self.NdO = packed.counts()
-                else:
-                    self.NO, self.NdO = n_loc, nbc_loc
-                self._pack = pack
-                self._factor()                                                  # solver.py:187-199 + LU of :305
+                    import torch.distributed as dist
+
+                    flag = torch.tensor([1.0 if loaded else 0.0], device=self._tdev)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.process_group)
+                    loaded = flag.item() > 0.5
+            if not loaded:
+                self._compute(x64)
                 if save:
                     self._save_precomputed()
             self._publish()
             torch.cuda.synchronize(self._dev_index)
+            if rng is not None:
+                lo_x, hi_x, lo_y, hi_y = rng.tolist()
+                assert lo_x >= 0 and hi_x <= 1, "x coordinates should be in [0, 1]. Please rescale."
+                assert lo_y >= 0 and hi_y <= 1, "y coordinates should be in [0, 1]. Please rescale."
+            if not loaded or self._refactor_pending:
+                self._finish_factor()
         self._ready = True
         t3 = time.perf_counter()
         if self.verbose > 0:
             print("\nPre-Computing Successful:", t3 - t0, "seconds")
 
+    def _calibrate(self, x64):
+        """Fit the fp16 operand scales of the tensor-core engine (and the fixed-point grid of DH) to this network /
+        domain on an evenly strided sample of 512 collocation points (grids come sorted)."""
+        if self._fdtype != torch.float32 or not x64[0].numel():
+            return
+        n_all = x64[0].numel()
+        if n_all > 512:
+            pick = torch.linspace(0, n_all - 1, 512, device=self._tdev).long()
+            xs, ys = x64[0][pick].contiguous(), x64[1][pick].contiguous()
+        else:
+            xs, ys = x64[0], x64[1]
+        _lib.check(self._lib.fps_calibrate_scales(self._ctx, xs.data_ptr(), ys.data_ptr(), xs.numel(), self._stream()),
+                   "fps_calibrate_scales")
+
+    def _compute(self, x64):
+        self._refactor_pending = False
+        st = self._stream()
+        lib, ctx = self._lib, self._ctx
+        n_loc, nbc_loc = x64[0].numel(), x64[2].numel()
+        self._calibrate(x64)
+        packed = PackedNormal(self._tdev)
+        self._pack = packed.buf
+        self._G64, self._Gbc64, self._s64 = packed.G, packed.Gbc, packed.s
+        self._xop_h = self._xop_dh = self._gplanes = self._rplanes_h = self._rplanes_dh = None
+        if self._exact(n_loc):
+            # cached exact-engine path: H / DH leave the feature kernel on their fixed-point grids, together with the
+            # digit planes of DH that the Gram and every later batched projection read (solver.py:162-167)
+            self._reserve(n_loc, 0)
+            self._Hp = torch.empty((n_loc, FP), dtype=torch.float32, device=self._tdev)
+            self._DHp = torch.empty((n_loc, FP), dtype=torch.float32, device=self._tdev)
+            xops = torch.zeros((2, _lib.XOP_BYTES // 4), dtype=torch.int32, device=self._tdev)
+            self._xop_h, self._xop_dh = xops[0], xops[1]
+            gbytes = int(lib.fps_gram_planes_bytes(n_loc))
+            self._gplanes = self._alloc_planes(gbytes) if self._want_cache(gbytes) else None
+            if self._gplanes is not None:
+                written = C.c_int(0)
+                _lib.check(lib.fps_features_x(ctx, x64[0].data_ptr(), x64[1].data_ptr(), n_loc, self._Hp.data_ptr(),
+                                              self._DHp.data_ptr(), FP, self._xop_h.data_ptr(), self._xop_dh.data_ptr(),
+                                              self._gplanes.data_ptr(), C.byref(written), st), "fps_features_x")
+                _lib.check(lib.fps_gram_accum_x(ctx, self._DHp.data_ptr(), n_loc, FP, self._xop_dh.data_ptr(),
+                                                self._gplanes.data_ptr(), written.value, self._G64.data_ptr(), st),
+                           "fps_gram_accum_x")
+            else:
+                # not enough memory to keep the planes: same arithmetic through the library's own pass workspace
+                _lib.check(lib.fps_features_x(ctx, x64[0].data_ptr(), x64[1].data_ptr(), n_loc, self._Hp.data_ptr(),
+                                              self._DHp.data_ptr(), FP, self._xop_h.data_ptr(), self._xop_dh.data_ptr(),
+                                              None, None, st), "fps_features_x")
+                _lib.check(lib.fps_gram_accum(ctx, self._DHp.data_ptr(), n_loc, FP, self._G64.data_ptr(), st),
+                           "fps_gram_accum")
+                self._xop_h = self._xop_dh = None    # later calls take the uncached entry points (same grids, same results)
+        else:
+            self._Hp, self._DHp = self._features(x64[0], x64[1], True)      # solver.py:162-166
+            if n_loc:
+                _lib.check(self._fn("fps_gram_accum")(ctx, self._DHp.data_ptr(), n_loc, FP, self._G64.data_ptr(), st),
+                           "fps_gram_accum")                                # solver.py:167
+        self._Hbcp, _ = self._features(x64[2], x64[3], False)               # solver.py:173-175
+        if nbc_loc:
+            _lib.check(self._fn("fps_gram_accum")(ctx, self._Hbcp.data_ptr(), nbc_loc, FP, self._Gbc64.data_ptr(), st),
+                       "fps_gram_accum(bc)")
+            _lib.check(self._fn("fps_colsum_accum")(ctx, self._Hbcp.data_ptr(), nbc_loc, FP, self._s64.data_ptr(), st),
+                       "fps_colsum_accum")                                  # solver.py:176-178
+        packed.set_counts(n_loc, nbc_loc)
+        if self.distributed:
+            packed.allreduce(self.process_group)  # the path's one exchange step
+            self._counts_dev = packed.buf[-2:]
+            self.NO = self.NdO = None              # read back with the final synchronise (see _publish)
+        else:
+            self.NO, self.NdO = n_loc, nbc_loc
+        self._factor()                                                      # solver.py:187-199 + LU of :305
+
     def _publish(self):
         """Expose reference attribute names as views / small casts of the device state."""
+        if self.NO is None:
+            c = self._counts_dev.cpu()
+            self.NO, self.NdO = int(round(c[0].item())), int(round(c[1].item()))
         self.H = self._Hp[:, :F]
         self.DH = self._DHp[:, :F]
         self.Dht = self.DH.t()
@@ -323,9 +418,19 @@ class Solver:
 
     # ---- precomputed-state persistence (solver.py:180-185, :201-207) ------------------------------
     def _save_precomputed(self):
+        torch.cuda.synchronize(self._dev_index)
+        self._finish_factor()
+        if self.NO is None:
+            c = self._counts_dev.cpu()
+            self.NO, self.NdO = int(round(c[0].item())), int(round(c[1].item()))
+        scales = (C.c_float * 24)()
+        _lib.check(self._lib.fps_get_scales(self._ctx, scales), "fps_get_scales")
         payload = {
-            "format": "fps_b200/2",
+            "format": _FORMAT, "dtype": str(self._fdtype), "FP": FP, "n": self._Hp.shape[0], "n_bc": self._Hbcp.shape[0],
+            "weights_sha256": self.weights_sha256, "act_scales": list(scales),
             "H": self._Hp.cpu(), "DH": self._DHp.cpu(), "H_bc": self._Hbcp.cpu(), "pack": self._pack.cpu(),
+            "xop_h": None if self._xop_h is None else self._xop_h.cpu(),
+            "xop_dh": None if self._xop_dh is None else self._xop_dh.cpu(),
             "L64": self._L64.cpu(), "NO": self.NO, "NdO": self.NdO, "lambdas": self.lambdas_pde, "jitter": self.jitter,
         }
         with open(self.precompute_file, "wb") as fh:
@@ -333,11 +438,25 @@ class Solver:
         if self.verbose > 0:
             print("Pre-Computed stored.")
 
-    def _load_precomputed(self):
-        with open(self.precompute_file, "rb") as fh:
-            p = pickle.load(fh)
-        if not isinstance(p, dict) or p.get("format") != "fps_b200/2":
-            raise _lib.FpsError(f"{self.precompute_file} was not written by this implementation")
+    def _load_precomputed(self, n_loc, nbc_loc):
+        """Returns False (-> recompute, as the reference does for a missing file) when the file does not describe this
+        Solver's problem: foreign format, other precision / weights / point counts."""
+        try:
+            with open(self.precompute_file, "rb") as fh:
+                p = pickle.load(fh)
+        except Exception:
+            return False
+        ok = (isinstance(p, dict) and p.get("format") == _FORMAT and p.get("dtype") == str(self._fdtype)
+              and p.get("FP") == FP and p.get("n") == n_loc and p.get("n_bc") == nbc_loc
+              and p.get("weights_sha256") == self.weights_sha256)
+        if ok:
+            ok = (tuple(p["H"].shape) == (n_loc, FP) and tuple(p["DH"].shape) == (n_loc, FP)
+                  and tuple(p["H_bc"].shape) == (nbc_loc, FP) and p["H"].dtype == self._fdtype
+                  and p["pack"].numel() == PackedNormal.SIZE)
+        if not ok:
+            if self.verbose > 0:
+                print(f"{self.precompute_file} does not match this Solver (format / precision / weights / points): recomputing.")
+            return False
         self._Hp, self._DHp, self._Hbcp = (p[k].to(self._tdev) for k in ("H", "DH", "H_bc"))
         pack = p["pack"].to(self._tdev)
         self._pack = pack
@@ -345,38 +464,66 @@ class Solver:
         self._Gbc64 = pack[FP * FP: 2 * FP * FP].view(FP, FP)
         self._s64 = pack[2 * FP * FP: 2 * FP * FP + FP]
         self.NO, self.NdO = p["NO"], p["NdO"]
+        self._xop_h = None if p.get("xop_h") is None else p["xop_h"].to(self._tdev)
+        self._xop_dh = None if p.get("xop_dh") is None else p["xop_dh"].to(self._tdev)
+        self._gplanes = self._rplanes_h = self._rplanes_dh = None   # rebuilt on demand from the stored (snapped) matrices
+        # the operand scales the stored H was produced with (evaluate() must reproduce the same features)
+        sc = (C.c_float * 24)(*p["act_scales"])
+        _lib.check(self._lib.fps_set_scales(self._ctx, sc), "fps_set_scales")
+        self._refactor_pending = False
         if list(p["lambdas"]) == list(self.lambdas_pde):
             self._L64, self.jitter = p["L64"].to(self._tdev), p["jitter"]
         else:
             self._factor()
+            self._refactor_pending = True
         if self.verbose > 0:
             print("Pre-Computed data_utils loaded from storage.")
+        return True
 
     # ---- solve -------------------------------------------------------------------------------------
     def _canon_rhs(self, f, bc):
         """Single RHS: anything with N (resp. N_bc) elements, flattened like utils.py:110-111.
-        Batched extension: f (N, B), bc (N_bc, B) or B constants."""
+        Batched extension: f (N, B), bc (N_bc, B) or B constants (one constant Dirichlet value per right-hand side)."""
         n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
         ft = f if isinstance(f, torch.Tensor) else torch.as_tensor(np.asarray(f))
         bt = bc if isinstance(bc, torch.Tensor) else torch.as_tensor(np.asarray(bc))
         ft = ft.to(self._tdev)
         bt = bt.to(self._tdev)
-        if ft.numel() == n_loc:
+        if ft.numel() == n_loc and not (ft.dim() == 2 and ft.shape[0] == n_loc and ft.shape[1] != 1):
             B = 1
             ft = ft.reshape(n_loc, 1)
         elif ft.dim() == 2 and ft.shape[0] == n_loc:
             B = ft.shape[1]
         else:
             raise ValueError(f"f has shape {tuple(ft.shape)}; expected {n_loc} values or ({n_loc}, B)")
-        if B == 1:
-            bt = bt.reshape(-1, 1)
-        elif bt.dim() == 2 and bt.shape == (nbc_loc, B):
-            pass
+        if bt.numel() == nbc_loc * B and (B == 1 or (bt.dim() == 2 and bt.shape == (nbc_loc, B))):
+            bt = bt.reshape(nbc_loc, B)
         elif bt.numel() == B:
-            bt = bt.reshape(1, B).expand(nbc_loc, B)
+            bt = bt.reshape(1, B).expand(nbc_loc, B)        # B constants (B = 1: a scalar boundary value)
         else:
-            raise ValueError(f"bc has shape {tuple(bt.shape)}; expected ({nbc_loc}, {B}) or {B} constants")
+            raise ValueError(f"bc has shape {tuple(bt.shape)}; expected {nbc_loc} values"
+                             + (f", ({nbc_loc}, {B})" if B > 1 else "") + f" or {B} constant(s)")
         return ft.to(self._fdtype).contiguous(), bt, B
+
+    def _ensure_recon_planes(self):
+        """Feature-major digit planes of H and DH for the batched reconstruction: built once per precompute, on the
+        first batched solve (a pure cache: H and DH already lie on their grids, nothing is modified)."""
+        if self._rplanes_h is not None or self._xop_h is None or self._rplanes_h is False:
+            return
+        n_loc = self._DHp.shape[0]
+        nbytes = int(self._lib.fps_recon_planes_bytes(n_loc))
+        if not self._want_cache(2 * nbytes):
+            self._rplanes_h = self._rplanes_dh = False
+            return
+        ph, pdh = self._alloc_planes(nbytes), self._alloc_planes(nbytes)
+        if ph is None or pdh is None:
+            self._rplanes_h = self._rplanes_dh = False
+            return
+        st = self._stream()
+        for A, xop, pl in ((self._Hp, self._xop_h, ph), (self._DHp, self._xop_dh, pdh)):
+            _lib.check(self._lib.fps_recon_planes_build(self._ctx, A.data_ptr(), n_loc, FP, xop.data_ptr(), 0,
+                                                        pl.data_ptr(), st), "fps_recon_planes_build")
+        self._rplanes_h, self._rplanes_dh = ph, pdh
 
     def solve(self, f, bc):
         if not self._ready:
@@ -385,57 +532,47 @@ class Solver:
             F32, BC, B = self._canon_rhs(f, bc)
             self.f, self.bc = F32.to(self.precision), BC.to(self.precision)
             st = self._stream()
+            lib, ctx = self._lib, self._ctx
             n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
+            exact = self._exact(n_loc) and B >= _MIN_B_EXACT and self._xop_dh is not None
+            if exact:
+                self._reserve(n_loc, B)
+                self._ensure_recon_planes()
             torch.cuda.synchronize(self._dev_index)
             t0 = time.perf_counter()
 
-            R = torch.zeros((FP, B), dtype=torch.float64, device=self._tdev)
+            # projected right-hand sides and (last row) the boundary sums: one buffer, one all-reduce
+            RS = torch.zeros((FP + 1, B), dtype=torch.float64, device=self._tdev)
+            R = RS[:FP]
             if n_loc:
-                _lib.check(self._fn("fps_project_rhs")(self._ctx, self._DHp.data_ptr(), n_loc, FP, F32.data_ptr(),
-                                                     F32.stride(0), B, R.data_ptr(), B, st), "fps_project_rhs")  # :301
-            sum_bc = BC.to(torch.float64).sum(dim=0).contiguous()                                               # :302
+                if exact and self._gplanes is not None:
+                    _lib.check(lib.fps_project_rhs_x(ctx, self._xop_dh.data_ptr(), self._gplanes.data_ptr(), n_loc,
+                                                     F32.data_ptr(), F32.stride(0), B, R.data_ptr(), B, st),
+                               "fps_project_rhs_x")                                                            # :301
+                else:
+                    _lib.check(self._fn("fps_project_rhs")(ctx, self._DHp.data_ptr(), n_loc, FP, F32.data_ptr(),
+                                                         F32.stride(0), B, R.data_ptr(), B, st), "fps_project_rhs")
+            RS[FP] = BC.to(torch.float64).sum(dim=0)                                                             # :302
             if self.distributed:
-                self._allreduce(R)
-                self._allreduce(sum_bc)
+                self._allreduce(RS)
+            sum_bc = RS[FP]
             U = torch.empty((n_loc + nbc_loc, B), dtype=self._fdtype, device=self._tdev)
             Fp = torch.empty((n_loc, B), dtype=self._fdtype, device=self._tdev)
             W = torch.empty((FP, B), dtype=torch.float64, device=self._tdev)
             bias = torch.empty(B, dtype=torch.float64, device=self._tdev)
             best = None
             for i, lam in enumerate(self.lambdas_pde):
-                _lib.check(self._lib.fps_solve_factored(self._ctx, self._L64[i].data_ptr(), R.data_ptr(), B, B,
-                                                        float(lam) / self.NO, self._s64.data_ptr(), sum_bc.data_ptr(),
-                                                        self.NdO, W.data_ptr(), bias.data_ptr(), st),
+                _lib.check(lib.fps_solve_factored(ctx, self._L64[i].data_ptr(), R.data_ptr(), B, B,
+                                                  float(lam) / self.NO, self._s64.data_ptr(), sum_bc.data_ptr(),
+                                                  self.NdO, W.data_ptr(), bias.data_ptr(), st),
                            "fps_solve_factored")                                                                # :305-306
-                self._reconstruct(W, bias, B, U, Fp, st)                                                         # :327-331
+                self._reconstruct(W, bias, B, U, Fp, st, exact)                                                  # :327-331
                 if self.n_lambdas > 1:
-                    # loss sweep of solver.py:309-317 (per right-hand side)
-                    l_pde = ((Fp.double() - F32.double()) ** 2).sum(dim=0)
-                    l_bc = ((U[n_loc:].double() - BC.double()) ** 2).sum(dim=0)
-                    cnt = torch.tensor([float(n_loc), float(nbc_loc)], dtype=torch.float64, device=self._tdev)
-                    if self.distributed:
-                        self._allreduce(l_pde)
-                        self._allreduce(l_bc)
-                        self._allreduce(cnt)
-                    l_pde, l_bc = l_pde / cnt[0], l_bc / cnt[1]
-                    self.Ls_pde[i], self.Ls_bc[i] = l_pde[0].item(), l_bc[0].item()
-                    self.Ls[i] = self.Ls_pde[i] + self.Ls_bc[i]
-                    tot = l_pde + l_bc
-                    if best is None:
-                        best = (tot.clone(), U.clone(), Fp.clone(), W.clone(), bias.clone(),
-                                torch.zeros(B, dtype=torch.long, device=self._tdev))
-                    else:
-                        take = tot < best[0]
-                        best[0][take] = tot[take]
-                        best[1][:, take] = U[:, take]
-                        best[2][:, take] = Fp[:, take]
-                        best[3][:, take] = W[:, take]
-                        best[4][take] = bias[take]
-                        best[5][take] = i
+                    best = self._select_lambda(i, best, U, Fp, W, bias, F32, BC, B, st)
             if self.n_lambdas > 1:
                 _, U, Fp, W, bias, which = best
-                self.lambda_pde = self.lambdas_pde[int(which[0].item())]
                 self.lambda_index = which
+                self.lambda_pde = self.lambdas_pde[int(which[0].item())]
             else:
                 self.lambda_pde = self.lambdas_pde[0]
 
@@ -452,9 +589,49 @@ class Solver:
             print("\nRun Successful:", t1 - t0, "seconds\n")
         return self.u_pred, self.u_pde_pred, self.u_bc_pred, self.f_pred, t1 - t0
 
+    def _select_lambda(self, i, best, U, Fp, W, bias, F32, BC, B, st):
+        """Loss sweep of solver.py:309-325 per right-hand side: mean squared PDE residual + mean squared boundary
+        residual (fps_sse_columns), smallest total wins."""
+        n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
+        sse = torch.zeros((2, B), dtype=torch.float64, device=self._tdev)
+        fn = self._fn("fps_sse_columns")
+        if n_loc:
+            _lib.check(fn(self._ctx, Fp.data_ptr(), Fp.stride(0), F32.data_ptr(), F32.stride(0), None, n_loc, B,
+                          sse[0].data_ptr(), st), "fps_sse_columns(pde)")
+        if nbc_loc:
+            Ub = U[n_loc:]
+            if BC.stride(0) == 0:      # B constants
+                bcc = BC[0].to(torch.float64).contiguous()
+                _lib.check(fn(self._ctx, Ub.data_ptr(), Ub.stride(0), None, 0, bcc.data_ptr(), nbc_loc, B,
+                              sse[1].data_ptr(), st), "fps_sse_columns(bc)")
+            else:
+                BCc = BC.to(self._fdtype).contiguous()
+                _lib.check(fn(self._ctx, Ub.data_ptr(), Ub.stride(0), BCc.data_ptr(), BCc.stride(0), None, nbc_loc, B,
+                              sse[1].data_ptr(), st), "fps_sse_columns(bc)")
+        cnt = torch.tensor([[float(n_loc)], [float(nbc_loc)]], dtype=torch.float64, device=self._tdev)
+        if self.distributed:
+            both = torch.cat([sse, cnt.expand(2, 1)], dim=1)
+            self._allreduce(both)
+            sse, cnt = both[:, :B], both[:, B:]
+        loss = sse / cnt
+        first = loss[:, 0].tolist()
+        self.Ls_pde[i], self.Ls_bc[i] = first
+        self.Ls[i] = first[0] + first[1]
+        tot = loss[0] + loss[1]
+        if best is None:
+            return (tot, U.clone(), Fp.clone(), W.clone(), bias.clone(), torch.zeros(B, dtype=torch.long, device=self._tdev))
+        take = tot < best[0]
+        best[0][take] = tot[take]
+        best[1][:, take] = U[:, take]
+        best[2][:, take] = Fp[:, take]
+        best[3][:, take] = W[:, take]
+        best[4][take] = bias[take]
+        best[5][take] = i
+        return best
+
     def evaluate(self, x, y):
         """Extension: the last solution u(x, y) = H(x, y) w + b at arbitrary points of [0,1]^2, (n, B)."""
-        if not hasattr(self, "_W64"):
+        if getattr(self, "_W64", None) is None:
             raise RuntimeError("call solve() before evaluate()")
         with torch.cuda.device(self._dev_index):
             x64, y64 = _as_f64_column(x, self._tdev), _as_f64_column(y, self._tdev)
@@ -466,14 +643,20 @@ class Solver:
                        "fps_reconstruct(evaluate)")
             return out.to(self.precision)
 
-    def _reconstruct(self, W, bias, B, U, Fp, st):
+    def _reconstruct(self, W, bias, B, U, Fp, st, exact=False):
         n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
         lib, ctx = self._lib, self._ctx
         if n_loc:
-            _lib.check(self._fn("fps_reconstruct")(ctx, self._Hp.data_ptr(), n_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
-                                           U.data_ptr(), B, st), "fps_reconstruct(u_pde)")
-            _lib.check(self._fn("fps_reconstruct")(ctx, self._DHp.data_ptr(), n_loc, FP, W.data_ptr(), B, None, B,
-                                           Fp.data_ptr(), B, st), "fps_reconstruct(f)")
+            if exact and self._rplanes_h not in (None, False):
+                _lib.check(lib.fps_reconstruct_x(ctx, self._xop_h.data_ptr(), self._rplanes_h.data_ptr(), n_loc, W.data_ptr(),
+                                                 B, bias.data_ptr(), B, U.data_ptr(), B, st), "fps_reconstruct_x(u_pde)")
+                _lib.check(lib.fps_reconstruct_x(ctx, self._xop_dh.data_ptr(), self._rplanes_dh.data_ptr(), n_loc,
+                                                 W.data_ptr(), B, None, B, Fp.data_ptr(), B, st), "fps_reconstruct_x(f)")
+            else:
+                _lib.check(self._fn("fps_reconstruct")(ctx, self._Hp.data_ptr(), n_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
+                                                       U.data_ptr(), B, st), "fps_reconstruct(u_pde)")
+                _lib.check(self._fn("fps_reconstruct")(ctx, self._DHp.data_ptr(), n_loc, FP, W.data_ptr(), B, None, B,
+                                                       Fp.data_ptr(), B, st), "fps_reconstruct(f)")
         if nbc_loc:
             _lib.check(self._fn("fps_reconstruct")(ctx, self._Hbcp.data_ptr(), nbc_loc, FP, W.data_ptr(), B, bias.data_ptr(), B,
-                                           U[n_loc:].data_ptr(), B, st), "fps_reconstruct(u_bc)")
+                                                   U[n_loc:].data_ptr(), B, st), "fps_reconstruct(u_bc)")

@@ -51,3 +51,75 @@ def sine_sources(solver, params, x=None, y=None, out=None) -> torch.Tensor:
     _lib.check(fn(solver._ctx, x64.data_ptr(), y64.data_ptr(), n, pd.data_ptr(), T, B, out.data_ptr(), out.stride(0),
                   solver._stream()), "fps_sine_sources")
     return out
+
+
+# ---- Perlin family (data_utils/source_functions.py:173-227) ------------------------------------------------
+# The reference sums 1-5 layers of the `perlin_noise` package's gradient noise (octaves ~ U(0.1,12), amplitude
+# ~ U(-100,100), one integer seed per layer) and, with probability 0.7, multiplies the sum by one more layer
+# (octaves ~ U(0.1,3), amplitude ~ U(-1,1)).  That package is a per-point Python loop and is absent here; sources are
+# INPUTS to the path, so the generator below keeps the family (same parameter draws, same quintic fade, same
+# lattice-gradient construction, coordinates scaled by `octaves`) but draws its lattice gradients from an integer
+# hash, which the device kernel (csrc/sources.cu: perlin_sources_kernel) evaluates identically.
+PERLIN_LAYERS = 5          # rows 0..4 of a parameter block: additive layers {octave, amplitude, seed}
+PERLIN_ROWS = 6            # row 5: multiplicative modulation layer (amplitude 0 = none)
+
+
+def perlin_params(B: int, seed: int = 0) -> np.ndarray:
+    """(B, 6, 3) float64: rows 0..4 additive layers {octave, amplitude, seed} (amplitude 0 = unused), row 5 the
+    modulation layer of source_functions.py:213-220 (amplitude 0 = not applied)."""
+    rng = np.random.default_rng(seed)
+    p = np.zeros((B, PERLIN_ROWS, 3))
+    for j in range(B):
+        n = int(rng.integers(1, PERLIN_LAYERS + 1))
+        p[j, :n, 0] = rng.uniform(0.1, 12.0, n)
+        p[j, :n, 1] = rng.uniform(-100.0, 100.0, n)
+        p[j, :n, 2] = rng.integers(1, 1000000, n)
+        if rng.random() > 0.3:
+            p[j, 5] = (rng.uniform(0.1, 3.0), rng.uniform(-1.0, 1.0), rng.integers(1, 1000000))
+    return p
+
+
+def _lattice_hash(ix, iy, seed):
+    """32-bit integer mix of a lattice point and a layer seed (uint32 wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        h = (ix.astype(np.uint32) * np.uint32(0x9E3779B1)) ^ (iy.astype(np.uint32) * np.uint32(0x85EBCA77)) \
+            ^ (np.uint32(seed) * np.uint32(0xC2B2AE3D))
+        h ^= h >> np.uint32(16)
+        h *= np.uint32(0x7FEB352D)
+        h ^= h >> np.uint32(15)
+        h *= np.uint32(0x846CA68B)
+        h ^= h >> np.uint32(16)
+    return h
+
+
+def _perlin_layer(x, y, octave, seed):
+    px, py = x * octave, y * octave
+    fx0, fy0 = np.floor(px), np.floor(py)
+    ix, iy = fx0.astype(np.int64), fy0.astype(np.int64)
+    fx, fy = px - fx0, py - fy0
+    sx = fx * fx * fx * (fx * (fx * 6.0 - 15.0) + 10.0)
+    sy = fy * fy * fy * (fy * (fy * 6.0 - 15.0) + 10.0)
+
+    def corner(dx, dy):
+        ang = _lattice_hash(ix + dx, iy + dy, int(seed)).astype(np.float64) * (2.0 * np.pi / 4294967296.0)
+        return np.cos(ang) * (fx - dx) + np.sin(ang) * (fy - dy)
+
+    n00, n10, n01, n11 = corner(0, 0), corner(1, 0), corner(0, 1), corner(1, 1)
+    return (n00 * (1.0 - sx) + n10 * sx) * (1.0 - sy) + (n01 * (1.0 - sx) + n11 * sx) * sy
+
+
+def perlin_sources_numpy(x, y, params) -> np.ndarray:
+    """(n, B) float64: host mirror of fps_perlin_sources."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    out = np.zeros((x.size, params.shape[0]))
+    for j, blk in enumerate(params):
+        u = np.zeros_like(x)
+        for octave, amp, seed in blk[:PERLIN_LAYERS]:
+            if amp != 0.0:
+                u += amp * _perlin_layer(x, y, octave, seed)
+        octave, amp, seed = blk[5]
+        if amp != 0.0:
+            u *= amp * _perlin_layer(x, y, octave, seed)
+        out[:, j] = u
+    return out

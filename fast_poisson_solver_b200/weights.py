@@ -100,3 +100,13 @@ class HostWeights:
         for i, k in enumerate(HIDDEN_KEYS):
             self.struct.h_wh[i] = p(k + ".weight")
             self.struct.h_bh[i] = p(k + ".bias")
+
+    def sha256(self) -> str:
+        """Identity of the weights the feature matrices were computed with (stored in saved precompute state)."""
+        import hashlib
+
+        h = hashlib.sha256()
+        for k in sorted(self.arrays):
+            h.update(k.encode())
+            h.update(self.arrays[k].tobytes())
+        return h.hexdigest()

@@ -14,8 +14,15 @@
  *   - stream is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
  *     unless stated;
  *   - return value 0 = ok, non-zero = error; fps_last_error() gives the message (per thread);
- *   - one host thread per context; a context owns its packed weights and a point-chunk workspace,
- *     nothing else is allocated by the library.
+ *   - one host thread per context and ONE stream at a time per context (the tile scheduler counters and the
+ *     workspaces below are not shared-safe);
+ *   - allocation: a context owns its packed weights, the activation workspace of one point wave, and grow-only
+ *     scratch of the exact int8 engine (digit planes of the right-hand sides F and of the weights W, split-K partial
+ *     tiles; the uncached entry points fps_gram_accum / fps_project_rhs / fps_reconstruct also keep the digit planes of
+ *     up to 2^20 rows of their matrix there).  Growing such a buffer calls cudaFree + cudaMalloc, which synchronises
+ *     the device: call fps_reserve_workspace(ctx, n, B) once per problem size and nothing allocates afterwards.
+ *     fps_workspace_bytes() reports the current total.  The cached entry points (suffix _x) keep their large operands
+ *     in CALLER-owned buffers.
  */
 #ifndef FPS_SM100_H
 #define FPS_SM100_H
@@ -35,7 +42,8 @@ extern "C" {
 #define FPS_NHIDDEN 5    /* depth-1 Linear(700,700)+Tanh blocks, model.py:49-60               */
 
 #define FPS_ENGINE_SIMT 0     /* fp32 FFMA layer kernel (bring-up / cross-check engine)        */
-#define FPS_ENGINE_TCGEN05 1  /* 3xTF32 tcgen05/TMEM/TMA layer kernel (production engine)      */
+#define FPS_ENGINE_TCGEN05 1  /* tcgen05/TMEM/TMA layer kernel, fp16 hi/lo operand planes (production engine) */
+#define FPS_XOP_BYTES 16384   /* size of one exact-operand descriptor (see "cached exact-engine operands")  */
 
 typedef struct fps_ctx fps_ctx;
 
@@ -67,6 +75,14 @@ int fps_set_engine(fps_ctx* ctx, int engine);
  * fps_get_scales copies the 6 x 4 scales out (host float[24]).                                       */
 int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t n, void* stream);
 int fps_get_scales(const fps_ctx* ctx, float* h_out24);
+/* Restore scales taken with fps_get_scales (a saved precompute state must be evaluated with the scales it was built with). */
+int fps_set_scales(fps_ctx* ctx, const float* h_in24);
+/* The same call (a) records max |DH| per feature over the sample, from which fps_features_x derives the fixed-point grid
+ * of its fused digit split, and (b) once per context checks the tensor-core kernel's accumulator-gain compensation
+ * (csrc/layer_tc.cu) against the fp32 FFMA engine on the sample, switching it off for weight sets where it hurts.
+ * fps_get_calibration: h_out5 = {rel-L2 of H, DH vs the fp32 engine with the compensation, the same without,
+ * 1 = compensation in use / 0 = switched off / -1 = not checked yet}.                                               */
+int fps_get_calibration(const fps_ctx* ctx, double* h_out5);
 int fps_get_engine(const fps_ctx* ctx);
 size_t fps_workspace_bytes(const fps_ctx* ctx);
 
@@ -85,9 +101,7 @@ int fps_features(fps_ctx* ctx, const double* x, const double* y, int64_t n,
  * below 2^-7 of their column maximum move by less than 2^-31 of that maximum (under 1 % of one
  * fp32 ulp of the maximum), all others are unchanged, and G64 receives the Gram of the stored A
  * to fp64 rounding.  Call it before anything else consumes A (fps_project_rhs, fps_reconstruct).
- * When A is the DH buffer of the latest fps_features call on this context (same pointer, same n),
- * the column maxima recorded by that call are used instead of a separate pass over A: do not
- * modify the buffer between the two calls.                                                      */
+ * The column maxima are taken in a pass over A inside the call (no state is kept between calls).  */
 int fps_gram_accum(fps_ctx* ctx, float* A, int64_t n, int64_t ld, double* G64, void* stream);
 
 /* Replaces `Ht_bc @ ones` (solver.py:176-178): s64 (FPS_FP) float64 += column sums of A.        */
@@ -106,6 +120,13 @@ int fps_colsum_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double
 int fps_assemble_factor(fps_ctx* ctx, const double* G64, const double* Gbc64, const double* s64,
                         int64_t n_total, int64_t nbc_total, const double* h_lambdas,
                         const double* h_jitter, int n_lambda, double* L64, int* info, void* stream);
+
+/* The same on the packed normal-equation buffer that the path's one all-reduce carries (FPS_PACK_DOUBLES float64:
+ * [G (FP*FP) | Gbc (FP*FP) | s (FP) | N | N_bc]): the point counts are read on the device, so a multi-GPU caller needs
+ * no host round trip between the all-reduce and the factorisation.                                               */
+#define FPS_PACK_DOUBLES (2 * FPS_FP * FPS_FP + FPS_FP + 2)
+int fps_assemble_factor_packed(fps_ctx* ctx, const double* pack64, const double* h_lambdas, const double* h_jitter,
+                               int n_lambda, double* L64, int* info, void* stream);
 
 /* Replaces `RHSs @ f` (solver.py:197 + :301) for B right-hand sides at once:
  * R64 (FPS_FP, ldr) float64 += DH^T F,  DH (n, ld) float32,  F (n, ldf) float32, B columns.
@@ -136,6 +157,50 @@ int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double*
 
 /* Multi-lambda loss of solver.py:312-314 for one lambda: loss64[0] = mean((pred-ref)^2).        */
 int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream);
+/* The same for B right-hand sides at once (the batched multi-lambda sweep): sse64[j] += sum_i (pred[i][j] - ref[i][j])^2,
+ * j < B; pred (n, ldp), ref (n, ldr) float32.  ref_const != NULL: ref[i][j] = ref_const[j] (float64; constant boundary
+ * values) and ref / ldr are ignored.  Accumulating (zero sse64 first); fixed summation order.                          */
+int fps_sse_columns(fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr,
+                    const double* ref_const, int64_t n, int B, double* sse64, void* stream);
+int fps_sse_columns_f64(fps_ctx* ctx, const double* pred, int64_t ldp, const double* ref, int64_t ldr,
+                        const double* ref_const, int64_t n, int B, double* sse64, void* stream);
+
+/* ---- cached exact-engine operands (n >= fps_exact_min_rows(); precision = float32) --------------------------------
+ * Gram, batched projection and batched reconstruction run on the int8 tensor cores with exact integer products
+ * (csrc/gram_i8.cu, csrc/recon_i8.cu).  Their operands are fixed-point images of H / DH: an exact-operand descriptor
+ * ("xop": FPS_XOP_BYTES of caller-owned device memory holding the per-feature exponents, scales and maxima) plus
+ * digit planes, also caller-owned:
+ *   gram planes   point-major  [128-point slab][4 digits][768][128]   fps_gram_planes_bytes(n)   Gram + projection
+ *   recon planes  feature-major [4 digits][n padded to 64][704]       fps_recon_planes_bytes(n)  reconstruction
+ * Keeping them between calls is what makes thousands of solves on one domain cheap; a caller short of memory uses
+ * the uncached entry points above instead (same results bit for bit, the planes are rebuilt per call).
+ *
+ * fps_features_x = fps_features for PDE points, plus: H is snapped to the uniform 2^-30 grid (|H| <= 1), xop_h / xop_dh
+ * are initialised, max |DH| per feature is recorded, and - tcgen05 engine, gram_planes != NULL, after
+ * fps_calibrate_scales - the last layer's epilogue itself snaps DH to the calibrated grid and writes DH's gram planes
+ * (*h_planes_written = 1).  An element beyond the calibrated grid raises a device flag; fps_gram_accum_x then rebuilds
+ * the grid from the true maxima and re-splits DH (device-side conditional, no host synchronisation).
+ * After fps_features_x + fps_gram_accum_x, H and DH never change again: solve() does not mutate precomputed state.  */
+int64_t fps_exact_min_rows(void);
+size_t fps_gram_planes_bytes(int64_t n);
+size_t fps_recon_planes_bytes(int64_t n);
+int fps_reserve_workspace(fps_ctx* ctx, int64_t n, int B);
+int fps_features_x(fps_ctx* ctx, const double* x, const double* y, int64_t n, float* H, float* DH, int64_t ld,
+                   void* xop_h, void* xop_dh, void* gram_planes, int* h_planes_written, void* stream);
+/* Replaces `DH.t() @ DH` (solver.py:167): G64 += A^T A exactly, leaving A's gram planes in `planes` and A snapped to
+ * the grid in xop.  planes_written = the value fps_features_x returned for this matrix (0: split here).              */
+int fps_gram_accum_x(fps_ctx* ctx, float* A, int64_t n, int64_t ld, void* xop, void* planes, int planes_written,
+                     double* G64, void* stream);
+/* Replaces `RHSs @ f` (solver.py:301) for B right-hand sides from DH's cached gram planes: R64 += DH^T F.            */
+int fps_project_rhs_x(fps_ctx* ctx, const void* xop, const void* planes, int64_t n, const float* F, int64_t ldf,
+                      int B, double* R64, int64_t ldr, void* stream);
+/* Recon planes of A (H or DH) on the grid of xop; derive_grid != 0 computes that grid from A's column maxima first
+ * (a matrix that did not come from fps_features_x).  A is snapped in place (a no-op for an already snapped matrix).  */
+int fps_recon_planes_build(fps_ctx* ctx, float* A, int64_t n, int64_t ld, void* xop, int derive_grid, void* planes,
+                           void* stream);
+/* Replaces the GEMVs of solver.py:327-330 for B right-hand sides from cached recon planes: out = A W + bias.          */
+int fps_reconstruct_x(fps_ctx* ctx, const void* xop, const void* planes, int64_t n, const double* W64, int64_t ldw,
+                      const double* bias64, int B, float* out, int64_t ldo, void* stream);
 
 /* ---- precision = torch.float64 (tests/test_solverclass.py:65-68 in the reference) ---------------
  * Same contracts as the fp32 entry points above with every feature matrix, right-hand side and
@@ -157,6 +222,29 @@ int fps_sine_sources(fps_ctx* ctx, const double* x, const double* y, int64_t n, 
                      int n_terms, int B, float* F, int64_t ldf, void* stream);
 int fps_sine_sources_f64(fps_ctx* ctx, const double* x, const double* y, int64_t n, const double* params,
                          int n_terms, int B, double* F, int64_t ldf, void* stream);
+/* The 'perlin' family (data_utils/source_functions.py:173-227): params device (B, 6, 3) float64, rows 0..4 additive
+ * layers {octaves, amplitude, seed} (amplitude 0 = unused), row 5 the multiplicative modulation layer (:213-220;
+ * amplitude 0 = none).  Lattice gradients come from an integer hash (fast_poisson_solver_b200/sources.py mirrors it).   */
+int fps_perlin_sources(fps_ctx* ctx, const double* x, const double* y, int64_t n, const double* params, int B,
+                       float* F, int64_t ldf, void* stream);
+int fps_perlin_sources_f64(fps_ctx* ctx, const double* x, const double* y, int64_t n, const double* params, int B,
+                           double* F, int64_t ldf, void* stream);
+/* Problem geometry of the reference's generator (data.py:192-217): interior G x G grid (x fastest) and the 4G + 4
+ * boundary ring [bottom, top, left, right]; [first, first + n) selects a rank's shard.  float64 device outputs.       */
+int fps_grid_points(fps_ctx* ctx, int G, int64_t first_pde, int64_t n_pde, double* x_pde, double* y_pde,
+                    int64_t first_bc, int64_t n_bc, double* x_bc, double* y_bc, void* stream);
+
+/* ---- finite-difference accuracy oracle (numeric_solver.py:104-151 + diff_matrices.py:22-59) ------------------------
+ * Solves the reference's 5-point Dirichlet system on a Gx x Gy interior grid (spacings hx, hy) for B right-hand sides
+ * exactly, by type-I sine transforms evaluated as fp64 GEMMs (csrc/fd_dst.cu).  F, U: (Gx*Gy, ld) with grid point
+ * (iy, ix) in row iy*Gx + ix (data.py:192-198 ordering); bc (B) constant boundary values or NULL (= 0; general boundary
+ * data is folded into F by the caller, see fast_poisson_solver_b200/numeric.py).  work: fps_fd_workspace_bytes(Gx, Gy,
+ * batch) bytes of device scratch; batch < B processes the right-hand sides in groups.                                  */
+size_t fps_fd_workspace_bytes(int Gx, int Gy, int batch);
+int fps_fd_solve(fps_ctx* ctx, int Gx, int Gy, double hx, double hy, const double* F, int64_t ldf, const double* bc,
+                 int B, double* U, int64_t ldu, void* work, size_t work_bytes, void* stream);
+int fps_fd_solve_f32(fps_ctx* ctx, int Gx, int Gy, double hx, double hy, const float* F, int64_t ldf, const double* bc,
+                     int B, double* U, int64_t ldu, void* work, size_t work_bytes, void* stream);
 
 /* ---- instrumentation (bench.py / profiles) ----------------------------------------------------
  * fps_launch_count: number of kernels this library has launched in this process (all contexts).
