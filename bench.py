@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the fast-poisson-solver hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-strong] [--no-cpu]
     torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL)
 
 One step = one pass of the hot path over one batch of synthetic input:
@@ -11,11 +11,18 @@ square, 4100 boundary-ring points, Perlin source, constant Dirichlet value.  Wit
 owns its own 2^20 points (weak scaling); the Gram / boundary blocks are all-reduced once per
 precompute and the projected right-hand side once per solve.
 
-Prints ONE JSON line (rank 0).  `value` = points/s with inputs resident in HBM; `e2e` = the same step
-fed from pinned host buffers with the result copied back; `roofline` = the dominant kernel (hidden
-700x700 layer, tcgen05 3xTF32) timed live with CUDA events; `cpu_baseline` = the oracle's
-algorithm-faithful port of the reference (2 800 autograd sweeps) on this box's host cores;
-`batched_solve` = BASELINE configs[2] (4096 right-hand sides on a 512x512 grid).
+Prints ONE JSON line (rank 0):
+  value          points/s, inputs resident in HBM, per-kernel instrumentation OFF
+  e2e            the same step fed from pinned host buffers with the result copied back
+  roofline       the dominant kernel (hidden 700x700 layer) timed with CUDA events on its own stream in a second,
+                 instrumented pass over the same steps; peak = MEASURED_PEAKS.json
+  int8_peak      dense int8 tensor-core rate measured in this run (torch._int_mm 8192^3, burst + sustained): the
+                 denominator for the exact Gram / projection / reconstruction kernels
+  batched_solve  BASELINE configs[2] (4096 right-hand sides on a 512x512 grid) per rank
+  strong         BASELINE configs[2] with the right-hand sides sharded over the N GPUs, configs[3] (4.19 M points,
+                 L-shape, point-sharded) and configs[4] (16.7 M points + 4096 solves, FD accuracy on 2048^2) at N GPUs
+  multi_gpu_parity (N > 1) a point-sharded precompute + solve against the same problem on rank 0 alone
+  cpu_baseline   the oracle's algorithm-faithful port of the reference (2 800 autograd sweeps) on this box's host cores
 """
 from __future__ import annotations
 
@@ -37,10 +44,20 @@ GRID = 1024                      # configs[1]: 1024 x 1024 points
 N_POINTS = GRID * GRID
 FLOP_PER_POINT_HIDDEN = 2 * 4 * 700 * 700          # one hidden layer, 4 streams
 FLOP_PER_POINT_FEATURES = 2 * 4 * (400 * 700 + 5 * 700 * 700)  # 21.84 MFLOP/point
+WORKLOAD = "configs[1]: 1024x1024 scattered (Sobol) points, Perlin source, precompute + single solve"
+
+
+def bench_config(world, n_pts=N_POINTS):
+    """The `config` object of the JSON line - identical for both arms (--impl ours / reference)."""
+    return {"workload": WORKLOAD, "points_per_gpu": n_pts, "boundary_points": 4 * GRID + 4,
+            "weights": "default init, seed 0 (the pretrained final.pt is absent from the reference checkout)",
+            "lambda": 2 ** -12, "parallelism": f"points sharded x{world}, 1 all-reduce per precompute + 1 per solve",
+            "l2": "inputs (H, DH: 2.9 GB each) larger than L2; no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------
-# synthetic inputs
+# synthetic inputs (host side: the scrambled Sobol sequence of data.py:200-205 comes from scipy; everything else is
+# generated on the device, fast_poisson_solver_b200/sources.py)
 # ---------------------------------------------------------------------------------------------
 def sobol_points(n, seed):
     from scipy.stats import qmc
@@ -65,32 +82,11 @@ def grid_points(G):
     return xi.flatten(), yi.flatten(), xb, yb
 
 
-def perlin(x, y, seed=0, layers=3):
-    """Vectorised gradient noise, statistically like source_functions.py:173-227 (1-5 octave layers,
-    octaves ~ U(0.1,12), amplitude ~ U(-100,100)); values need not match the absent perlin_noise
-    package - sources are inputs to the path."""
-    rng = np.random.default_rng(seed)
-    out = np.zeros_like(x)
-    for _ in range(layers):
-        octv = rng.uniform(0.1, 12.0)
-        amp = rng.uniform(-100, 100)
-        n = int(np.ceil(octv)) + 2
-        ang = rng.uniform(0, 2 * np.pi, (n + 1, n + 1))
-        gx, gy = np.cos(ang), np.sin(ang)
-        px, py = x * octv, y * octv
-        ix, iy = np.floor(px).astype(np.int64), np.floor(py).astype(np.int64)
-        fx, fy = px - ix, py - iy
-        sx, sy = fx * fx * fx * (fx * (fx * 6 - 15) + 10), fy * fy * fy * (fy * (fy * 6 - 15) + 10)
+def perlin(x, y, seed=0):
+    """One Perlin-family source on the host (mirror of the device generator)."""
+    from fast_poisson_solver_b200.sources import perlin_params, perlin_sources_numpy
 
-        def dot(ax, ay, dx, dy):
-            return gx[ax, ay] * dx + gy[ax, ay] * dy
-
-        n00 = dot(ix, iy, fx, fy)
-        n10 = dot(ix + 1, iy, fx - 1, fy)
-        n01 = dot(ix, iy + 1, fx, fy - 1)
-        n11 = dot(ix + 1, iy + 1, fx - 1, fy - 1)
-        out += amp * ((n00 * (1 - sx) + n10 * sx) * (1 - sy) + (n01 * (1 - sx) + n11 * sx) * sy)
-    return out
+    return perlin_sources_numpy(x, y, perlin_params(1, seed=seed))[:, 0]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -165,14 +161,15 @@ def run_reference(args):
         _, threads = cpu_reference_step(n_sample)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     v = n_sample / dt
-    sample = (f"{n_sample} of the 2^20 scattered points + their ring, precompute+solve, oracle port of the reference "
-              f"algorithm (model.h + 2800 torch.autograd sweeps, fp32) on host cores")
+    sample = (f"each step = {n_sample} of the 2^20 scattered points + their ring, precompute+solve, oracle port of the "
+              f"reference algorithm (model.h + 2800 torch.autograd sweeps, fp32) on {threads} host threads; the reference "
+              f"is pure Python and cannot travel to the GPU box, its per-point cost is size-independent beyond ~1e3 points "
+              f"(SURVEY.md 6: 844 s for 1e4 points on 8 cores)")
     print(json.dumps({
         "impl": "reference", "metric": "precompute_points_per_s", "value": v, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1024x1024 scattered points, Perlin source, precompute + single solve",
-                   "sample": sample},
+        "config": bench_config(args.gpus, args.points),
         "cpu_baseline": {"value": v, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -195,12 +192,8 @@ def measure_peak(torch, dtype, n, tf32=False, reps=10):
             e1.record()
             e1.synchronize()
             best = min(best, e0.elapsed_time(e1))
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old
-    burst = 2.0 * n ** 3 / (best * 1e-3) / 1e12
-    # sustained: back to back for ~1.5 s under the power cap (MEASURED_PEAKS.json protocol)
-    torch.backends.cuda.matmul.allow_tf32 = tf32
-    try:
+        burst = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        # sustained: back to back for ~1.5 s under the power cap (MEASURED_PEAKS.json protocol)
         reps_s = max(10, int(1.5 / (best * 1e-3)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -214,6 +207,35 @@ def measure_peak(torch, dtype, n, tf32=False, reps=10):
     return burst, sustained
 
 
+def measure_int8_peak(torch, n=8192, reps=10):
+    """Dense int8 tensor-core rate (cuBLASLt through torch._int_mm), TOP/s: best of `reps` and back to back for ~1.5 s."""
+    try:
+        a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+        b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda").t().contiguous().t()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps_s = max(10, int(1.5 / (best * 1e-3)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps_s):
+            torch._int_mm(a, b)
+        e1.record()
+        e1.synchronize()
+        return {"burst_tops": 2.0 * n ** 3 / (best * 1e-3) / 1e12,
+                "sustained_tops": 2.0 * n ** 3 * reps_s / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch._int_mm {n}^3 (cuBLASLt int8 -> int32), best of {reps} / back to back for 1.5 s, this run"}
+    except Exception as exc:  # noqa: BLE001
+        return {"burst_tops": None, "sustained_tops": None, "how": f"torch._int_mm unavailable: {exc}"}
+
+
 def read_profile(solver):
     from fast_poisson_solver_b200 import _lib
 
@@ -222,6 +244,62 @@ def read_profile(solver):
         ms, n = C.c_double(), C.c_int64()
         _lib.check(solver._lib.fps_profile_read(solver._ctx, k, C.byref(ms), C.byref(n)), "fps_profile_read")
         out[name] = (ms.value, n.value)
+    return out
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture of this round (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        for k, v in t.items():
+            if kernel_substr in k:
+                return v
+    except Exception:
+        pass
+    return None
+
+
+def multi_gpu_parity(torch, dist, world, rank, local):
+    """A point-sharded precompute + batched and single solve over all ranks against the SAME problem solved on rank 0
+    alone (multi-GPU parity must be driver-visible).  20 736 points per rank: the exact int8 paths."""
+    from fast_poisson_solver_b200 import Solver
+    from fast_poisson_solver_b200.parallel import shard_bounds
+
+    G = int(round((20736 * world) ** 0.5))
+    xp, yp, xb, yb = grid_points(G)
+    B = 40
+    Fm = np.stack([(50.0 + j) * np.sin((2 + j % 4) * np.pi * xp) * np.sin((3 + (j // 4) % 3) * np.pi * yp) for j in range(B)], 1)
+    Fm[:, 1] = perlin(xp, yp, seed=3)
+    bcv = np.linspace(-2, 3, B)
+    lo, hi = shard_bounds(xp.size, rank, world)
+    blo, bhi = shard_bounds(xb.size, rank, world)
+    s = Solver(device=f"cuda:{local}", use_weights=False, distributed=True)
+    s.precompute(xp[lo:hi], yp[lo:hi], xb[blo:bhi], yb[blo:bhi])
+    u_pde = s.solve(Fm[lo:hi], np.tile(bcv[None], (bhi - blo, 1)))[1]
+    u1 = s.solve(Fm[lo:hi, 1], np.full(bhi - blo, bcv[1]))[1]
+    sizes = [shard_bounds(xp.size, r, world)[1] - shard_bounds(xp.size, r, world)[0] for r in range(world)]
+    mine = torch.zeros((max(sizes), B + 1), dtype=torch.float32, device=f"cuda:{local}")   # equal sizes for all_gather
+    mine[: hi - lo] = torch.cat([u_pde, u1], dim=1)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    out = None
+    if rank == 0:
+        full = torch.cat([g[:n] for g, n in zip(gathered, sizes)], dim=0).double()
+        ref = Solver(device=f"cuda:{local}", use_weights=False)
+        ref.precompute(xp, yp, xb, yb)
+        r_pde = ref.solve(Fm, bcv)[1].double()
+        r1 = ref.solve(Fm[:, 1], np.full(xb.size, bcv[1]))[1].double()
+        eb = max(float((full[:, j] - r_pde[:, j]).norm() / r_pde[:, j].norm()) for j in range(B))
+        e1 = float((full[:, B] - r1[:, 0]).norm() / r1[:, 0].norm())
+        out = {"points": int(xp.size), "rhs": B, "ranks": world, "worst_u_rel_l2_batched": eb, "u_rel_l2_single": e1,
+               "tolerance": 1e-6, "pass": bool(eb < 1e-6 and e1 < 1e-6),
+               "note": "same kernels and features; the summation order of the fp64 partial Grams / projections differs and "
+                       "every rank snaps its rows of DH to its own calibrated grid"}
+        del ref
+    del s
+    torch.cuda.empty_cache()
+    dist.barrier()
     return out
 
 
@@ -292,47 +370,98 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step_resident()
-    _lib.check(lib.fps_profile_enable(ctx, 1), "profile")
-    _lib.check(lib.fps_profile_reset(ctx), "profile")
+    # ---- headline: K steps, instrumentation OFF --------------------------------------------------
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
     launches0 = lib.fps_launch_count()
     ms_step = timed(step_resident, args.steps)
     launches = (lib.fps_launch_count() - launches0) // args.steps
+    clk = clocks.stop() if rank == 0 else None
+    # ---- the same steps again with per-kernel CUDA events (roofline of the dominant kernel, kernel breakdown) -----
+    _lib.check(lib.fps_profile_enable(ctx, 1), "profile")
+    _lib.check(lib.fps_profile_reset(ctx), "profile")
+    ms_step_prof = timed(step_resident, args.steps)
     prof = read_profile(solver)
     _lib.check(lib.fps_profile_enable(ctx, 0), "profile")
-    clk = clocks.stop() if rank == 0 else None
 
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    cal = (C.c_double * 5)()
+    lib.fps_get_calibration(ctx, cal)
+    planes_cached = solver._gplanes is not None
 
-    # ---- batched solve (configs[2]): 512x512 grid, B right-hand sides ---------------------------
+    # ---- batched solve (configs[2]): 512x512 grid, B right-hand sides PER RANK ---------------------------
     batched = None
     if args.batch > 0:
-        gx, gy, gxb, gyb = grid_points(512)
-        solver.precompute(d(gx, torch.float64), d(gy, torch.float64), d(gxb, torch.float64), d(gyb, torch.float64))
+        from bench_configs import mixed_sources
+        from fast_poisson_solver_b200.sources import grid_points as dev_grid_points
+
+        solver_b = Solver(device=f"cuda:{local}", use_weights=False, engine=args.engine)
+        gx, gy, gxb, gyb = dev_grid_points(solver_b, 512)
+        solver_b.precompute(gx, gy, gxb, gyb)
         B = args.batch
-        gen = torch.Generator(device=dev).manual_seed(rank)
-        base = d(np.stack([perlin(gx, gy, seed=s) for s in range(8)], 1), torch.float32)       # (n, 8)
-        mix = torch.randn(8, B, device=dev, generator=gen)
-        Fm = (base @ mix).contiguous()                                                          # (n, B) synthetic mixtures
-        bcv = (torch.rand(B, device=dev, generator=gen) * 20 - 10)
-        solver.solve(Fm, bcv)
-        _lib.check(lib.fps_profile_enable(ctx, 1), "profile")
-        _lib.check(lib.fps_profile_reset(ctx), "profile")
-        ms_b = timed(lambda: solver.solve(Fm, bcv), 3)
-        u_cols = solver.u_pde_pred[:, :4].double().cpu().numpy()
-        f_cols, bc_cols = Fm[:, :4].double().cpu().numpy(), bcv[:4].double().cpu().numpy()
-        pb = read_profile(solver)
-        _lib.check(lib.fps_profile_enable(ctx, 0), "profile")
+        Fm = mixed_sources(solver_b, B, seed=10 + rank)                     # Perlin + sine families, generated on the device
+        bcv = (torch.rand(B, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)) * 20 - 10)
+        solver_b.solve(Fm, bcv)
+        ms_b = timed(lambda: solver_b.solve(Fm, bcv), 3)
+        _lib.check(lib.fps_profile_enable(solver_b._ctx, 1), "profile")
+        _lib.check(lib.fps_profile_reset(solver_b._ctx), "profile")
+        timed(lambda: solver_b.solve(Fm, bcv), 3)
+        pb = read_profile(solver_b)
+        _lib.check(lib.fps_profile_enable(solver_b._ctx, 0), "profile")
+        u_cols = solver_b.u_pde_pred[:, [0, B - 1]].double()
+        f_cols, bc_cols = Fm[:, [0, B - 1]].double(), bcv[[0, B - 1]].double().cpu().numpy()
+        npts_b = gx.numel()
         batched = {"value": world * B / (ms_b * 1e-3), "unit": "solves/s", "ms_per_call": ms_b,
-                   "config": {"workload": "configs[2]: 4096 RHS on a 512x512 grid", "points": int(gx.size), "rhs": B,
-                              "sharding": "columns across ranks, features replicated, no collective"},
-                   "kernels_ms": {k: round(v[0] / 3, 3) for k, v in pb.items() if v[1]}}
-        del Fm
+                   "config": {"workload": "configs[2]: 4096 Perlin/sine RHS on a 512x512 grid", "points": int(npts_b), "rhs": B,
+                              "sharding": "B columns per rank, features replicated, no collective (strong form: `strong` block)"},
+                   "planes_cached": {"gram": solver_b._gplanes is not None, "recon": isinstance(solver_b._rplanes_h, torch.Tensor)},
+                   "kernels_ms": {k: round(v[0] / 3, 3) for k, v in pb.items() if v[1]},
+                   "issued_int8_tops": {
+                       # digit-pair products actually issued: projection 16 pairs (4 x 4 digits), reconstruction 20 (5 x 4)
+                       "project": 16 * 2.0 * 768 * ((B + 63) // 64 * 64) * npts_b / (pb["project"][0] / 3 * 1e-3) / 1e12 if pb["project"][0] else None,
+                       "reconstruct": 2 * 20 * 2.0 * 704 * ((B + 255) // 256 * 256) * npts_b / (pb["reconstruct"][0] / 3 * 1e-3) / 1e12 if pb["reconstruct"][0] else None}}
+        # accuracy oracle of north_star: the reference's finite-difference solve on the same 512x512 grid (GPU DST, pinned
+        # to the reference's numeric_solve by tests/golden/numeric_solve_seed0.npz), metrics as analyze.py:107-119
+        from fast_poisson_solver_b200.numeric import fd_solve_grid
+
+        u_fd = fd_solve_grid(solver_b, 512, 512, 1.0 / 513, 1.0 / 513, f_cols.contiguous(), bc=bc_cols)
+        acc = []
+        for j, fam in enumerate(("perlin", "sine")):
+            dlt = u_cols[:, j] - u_fd[:, j]
+            mae = float(dlt.abs().mean())
+            acc.append({"family": fam, "mse": float((dlt * dlt).mean()), "rmse": float((dlt * dlt).mean().sqrt()), "mae": mae,
+                        "rmae": mae / max(float(u_fd[:, j].abs().mean()), 1e-6), "rel_l2": float(dlt.norm() / u_fd[:, j].norm())})
+        batched["accuracy_vs_fd_512x512"] = acc
+        del Fm, solver_b
+        torch.cuda.empty_cache()
+
+    parity = multi_gpu_parity(torch, dist, world, rank, local) if world > 1 else None
+
+    # ---- peaks (rank 0 measures; the other ranks idle) ------------------------------------------------------
+    peaks, tf32_burst, tf32_peak, f64_burst, f64_peak, i8 = {}, None, None, None, None, None
+    if rank == 0:
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf32_burst, tf32_peak = measure_peak(torch, torch.float32, 8192, tf32=True)
+        f64_burst, f64_peak = measure_peak(torch, torch.float64, 4096)
+        i8 = measure_int8_peak(torch)
+    barrier()
+
+    # ---- strong-scaling target configurations --------------------------------------------------------------
+    strong = None
+    if args.strong:
+        from bench_configs import Env, strong_block
+
+        del solver
+        torch.cuda.empty_cache()
+        strong = strong_block(Env(), quick=args.quick)
 
     if world > 1:
         dist.barrier()
@@ -341,62 +470,54 @@ def run_ours(args):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----------------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    tf32_burst, tf32_peak = measure_peak(torch, torch.float32, 8192, tf32=True)
-    f16_fmt = os.environ.get("FPS_TC_F16", "1") != "0"
-    if f16_fmt:
-        # the FP16x2-split engine issues kind::f16 MMAs: the tensor roofline is the dense 16-bit peak of
-        # MEASURED_PEAKS.json (bf16 and fp16 share the rate); sustained figure, the kernel runs inside a long step
-        tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        tc_burst = float(peaks.get("bf16_tflops", 1590.0))
-        tc_src = ("dense 16-bit tensor peak from MEASURED_PEAKS.json (bf16_tflops_sustained; fp16 MMAs run at the same rate)"
-                  if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
-    else:
-        tc_peak, tc_burst = tf32_peak, tf32_burst
-        tc_src = "dense TF32 measured in this run (torch.matmul 8192^3, allow_tf32, sustained 1.5 s)"
-    f64_burst, f64_peak = measure_peak(torch, torch.float64, 4096)
+    # the FP16x2-split engine issues kind::f16 MMAs: the tensor roofline is the dense 16-bit peak of MEASURED_PEAKS.json
+    # (bf16 and fp16 share the rate); sustained figure, the kernel runs inside a long step
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tc_burst = float(peaks.get("bf16_tflops", 1590.0))
+    tc_src = ("dense 16-bit tensor peak from MEASURED_PEAKS.json (bf16_tflops_sustained; fp16 MMAs run at the same rate)"
+              if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     hid_ms, hid_n = prof["hidden"]
-    hid_flop = 4 * args.steps * n_pts * FLOP_PER_POINT_HIDDEN      # 4 hidden launches per chunk write planes
+    hid_flop = 4 * args.steps * n_pts * FLOP_PER_POINT_HIDDEN      # 4 hidden launches per wave write planes
     achieved = hid_flop / (hid_ms * 1e-3) / 1e12 if hid_ms else None
     kernels_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}
     feat_ms = sum(prof[k][0] for k in ("fourier", "layer0", "hidden", "last")) / args.steps
     gram_ms = prof["gram"][0] / args.steps
     gram_flop = 700 * 701 * (n_pts + xb.size)
+    gram_issued = (16 * 23 * 256 * 64 * 2 * ((n_pts + 127) // 128 * 128)) / (gram_ms * 1e-3) / 1e12 if gram_ms else None
+    i8_sus = i8.get("sustained_tops") if i8 else None
+    solve_ms = sum(prof[k][0] for k in ("project", "trisolve", "reconstruct")) / args.steps
     out = {
         "metric": "precompute_points_per_s", "value": world * n_pts / (ms_step * 1e-3), "unit": "points/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16x2-split(3 MMA) features + exact int8 (4-digit) Gram + f64 factor/solve",
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16x2-split(3 MMA) features + exact int8 (4-digit) Gram + f64 factor/solve",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: 1024x1024 scattered (Sobol) points, Perlin source, precompute + single solve",
-                   "points_per_gpu": n_pts, "boundary_points": int(xb.size) * world, "weights": "default init, seed 0",
-                   "engine": "tcgen05" if solver.engine == 1 else "simt", "lambda": 2 ** -12,
-                   "parallelism": f"points sharded x{world}, 1 all-reduce/precompute + 1/solve" if world > 1 else "single GPU",
-                   "l2": "inputs (H, DH: 2.9 GB each) larger than L2; no flush needed"},
+        "config": bench_config(world, n_pts),
         "e2e": {"value": world * n_pts / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clk,
+        "engine": {"features": "tcgen05" if solver_engine_is_tc(args) else "simt", "gram_planes_cached": planes_cached,
+                   "accumulator_gain_check": {"H_with": cal[0], "DH_with": cal[1], "H_without": cal[2], "DH_without": cal[3],
+                                              "gain_in_use": cal[4]}},
+        "ms_per_step_instrumented": ms_step_prof,
         "kernels_ms_per_step": kernels_ms,
-        "roofline": {"kernel": "layer_tc_pair_kernel<4,false,true> (hidden 700x700 layer, 4 streams, FP16x2-split tcgen05 cta_group::2)",
+        "roofline": {"kernel": "layer_tc_pair_kernel<4,false,true,128> (hidden 700x700 layer, 4 streams, FP16x2-split tcgen05 cta_group::2)",
                      "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": achieved / tc_peak if achieved else None,
                      "issued_frac": 3 * achieved * (768 / 700) * (704 / 700) / tc_peak if achieved else None,
                      "frac_ceiling": 1.0 / (3 * (768 / 700) * (704 / 700)),
                      "peak_burst": tc_burst, "tf32_peak_sustained_this_run": tf32_peak,
-                     "peak_source": tc_src + "; achieved = ALGORITHMIC flops (2*4*700*700 per point) / CUDA-event time; "
-                                    "fp32-grade products need 3 MMAs each and M is padded 700->768, so frac cannot "
-                                    "exceed frac_ceiling; issued_frac is the tensor-pipe share actually occupied",
+                     "peak_source": tc_src + "; achieved = ALGORITHMIC flops (2*4*700*700 per point) / CUDA-event time of the "
+                                    "instrumented pass; fp32-grade products need 3 MMAs each and M is padded 700->768, so frac "
+                                    "cannot exceed frac_ceiling; issued_frac is the tensor-pipe share actually occupied; the "
+                                    "kernel also sits at the L2->SM operand-feed cap (DESIGN.md section 4)",
                      "launches": int(hid_n), "avg_launch_ms": hid_ms / hid_n if hid_n else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
-                     # (profiles/r01d_layer_tc_ncu_full_summary.csv: 390.8 MB for an 18 944-point launch = 20.6 KB per
-                     # point; algorithmic: 11.3 KB in + 11.3 KB out per point + 2 MB of weights), scaled to the points
-                     # of one launch of this run
-                     "traffic": (20.6e3 if f16_fmt else 44.7e3) * (4 * args.steps * n_pts / hid_n) if hid_n else None,
-                     "traffic_unit": "bytes/launch (ncu, per-point figure x points per launch)"},
+                     "points_per_launch": 4 * args.steps * n_pts / hid_n if hid_n else None,
+                     "traffic": ncu_traffic("layer_tc_pair_kernel<4, false"),
+                     "traffic_unit": "bytes/launch: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                     "(profiles/r02_ncu_traffic.json); null = no capture committed for this build"},
+        "int8_peak": i8,
         "other_rooflines": {
             "features_all_layers": {"achieved": n_pts * FLOP_PER_POINT_FEATURES / (feat_ms * 1e-3) / 1e12,
                                     "peak": tc_peak, "unit": "TFLOP/s (algorithmic, 3 MMAs issued per product)"},
@@ -404,14 +525,25 @@ def run_ours(args):
             "gram_exact_int8": {"achieved": gram_flop / (gram_ms * 1e-3) / 1e12 if gram_ms else None,
                                 "unit": "TFLOP/s (algorithmic SYRK flops, fp64-exact result)",
                                 "fp64_pipe_peak": f64_peak, "fp64_pipe_peak_burst": f64_burst,
-                                "peak_source": "the fp64 pipe this path replaces: torch.matmul fp64 4096^3 sustained / "
-                                               "best of 10, this run; issued int8 work = 16 digit pairs x 23 tiles of 256 x 64 x 2 ops per point, "
-                                               "against a nominal 4.5 POP/s dense int8 peak; the time includes the digit split",
-                                "issued_int8_tops": (16 * 23 * 256 * 64 * 2 * ((n_pts + 127) // 128 * 128)) / (gram_ms * 1e-3) / 1e12
-                                if gram_ms else None},
+                                "issued_int8_tops": gram_issued,
+                                "issued_frac_of_measured_int8_peak": gram_issued / i8_sus if gram_issued and i8_sus else None,
+                                "note": "issued int8 work = 16 digit pairs x 23 tiles of 256 x 64 x 2 ops per point against the "
+                                        "int8 peak measured in this run; the digit split is fused into the last layer's epilogue"},
+            "single_solve_hbm": {"ms": solve_ms, "algorithmic_bytes": 8400 * n_pts,
+                                 "achieved_gbs": 8400 * n_pts / (solve_ms * 1e-3) / 1e9 if solve_ms else None,
+                                 "peak_gbs": float(peaks.get("hbm_gbs", 6545.6)),
+                                 "frac": 8400 * n_pts / (solve_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6545.6)) if solve_ms else None,
+                                 "note": "projection + triangular sweeps + reconstruction of one right-hand side; 8400 B/point = "
+                                         "DH twice + H once (SURVEY.md 8a8)"},
         },
         "batched_solve": batched,
+        "multi_gpu_parity": parity,
+        "strong": strong,
     }
+    if batched and i8_sus:
+        for k in ("project", "reconstruct"):
+            v = batched["issued_int8_tops"].get(k)
+            batched["issued_int8_tops"][k + "_frac_of_measured_peak"] = v / i8_sus if v else None
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ----------------------------------------
     if world == 1 and not args.no_cpu:
         n_sample = 512
@@ -423,19 +555,13 @@ def run_ours(args):
                       f"sweeps, fp32, precompute+solve) took {dt:.1f} s on {threads} threads of {os.cpu_count()} cores",
             "forward_mode_port_points_per_s": 10000 / dt_fwd,
         }
-        if batched is not None:
-            # accuracy oracle of north_star: the reference's finite-difference solve (numeric_solver.py:39-160,
-            # restated exactly by a DST in oracle/fd_oracle.py) on the 512x512 grid of the batched config,
-            # metrics as analyze.py:107-119
-            from oracle import fd_oracle, fps_oracle
-
-            u_fd = fd_oracle.fd_solve_dst(512, f_cols, bc_cols)
-            out["cpu_baseline"]["accuracy_vs_fd_512x512"] = [
-                dict(fps_oracle.metrics(u_cols[:, j], u_fd[:, j]), rel_l2=fps_oracle.rel_l2(u_cols[:, j], u_fd[:, j]))
-                for j in range(u_cols.shape[1])]
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def solver_engine_is_tc(args):
+    return args.engine == "tcgen05"
 
 
 def main():
@@ -448,6 +574,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--engine", default="tcgen05")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", dest="strong", action="store_false")
+    ap.add_argument("--quick", action="store_true", help="reduced sizes in the strong block (development)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

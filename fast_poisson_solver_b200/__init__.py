@@ -8,6 +8,7 @@
 Everything numerical runs in libfps_sm100.so (hand-written CUDA, C ABI in include/fps_sm100.h).
 """
 from .solver import Solver, format_input  # noqa: F401
+from .numeric import numeric_solve  # noqa: F401  (GPU restatement of the reference's FD accuracy oracle)
 
-__all__ = ["Solver", "format_input"]
-__version__ = "0.1.0"
+__all__ = ["Solver", "format_input", "numeric_solve"]
+__version__ = "0.2.0"

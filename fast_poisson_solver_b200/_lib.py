@@ -47,7 +47,7 @@ SIGNATURES = {
     "fps_get_engine": (_i32, [_vp]),
     "fps_calibrate_scales": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "fps_get_scales": (_i32, [_vp, C.POINTER(C.c_float)]),
-    "fps_set_scales": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "fps_set_calibration": (_i32, [_vp, C.POINTER(C.c_float), _i32]),
     "fps_get_calibration": (_i32, [_vp, C.POINTER(_f64)]),
     "fps_workspace_bytes": (C.c_size_t, [_vp]),
     "fps_features": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),

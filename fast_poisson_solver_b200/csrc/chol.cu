@@ -216,7 +216,7 @@ __device__ __forceinline__ void cf_grid_barrier(unsigned* counter, unsigned& tar
     atomicAdd(counter, 1u);
     unsigned spins = 0;
     while (*reinterpret_cast<volatile unsigned*>(counter) < target) {
-      if (++spins > 400000000u) {
+      if (++spins > 20000000u) {
         printf("fps chol_fused: grid barrier timeout (block %d target %u)\n", blockIdx.x, target);
         __trap();
       }
@@ -232,6 +232,7 @@ chol_fused_kernel(const double* __restrict__ G, const double* __restrict__ Gbc, 
                   double* __restrict__ L, double* __restrict__ Dfac, unsigned long long* __restrict__ dmax_bits,
                   unsigned* __restrict__ bar, int* __restrict__ info) {
   __shared__ double D[CB][CB + 1];
+  __shared__ double Dr[CB];            // reciprocals of the diagonal of the factored block
   __shared__ double Pi[64][CB + 1];
   __shared__ double Pj[64][CB + 1];
   __shared__ double red[8];
@@ -281,14 +282,15 @@ chol_fused_kernel(const double* __restrict__ G, const double* __restrict__ Gbc, 
         double d = D[j][j];
         const bool bad = !(d > tol);
         if (bad) d = safe;  // keep the arithmetic finite; the host sees info != 0 and retries with a shift
-        const double ljj = sqrt(d);
+        const double rs = rsqrt(d);          // the serial chain of 704 columns: one rsqrt + multiplies, no divisions
         __syncthreads();
         if (t < CB) {
           if (t == j) {
-            D[j][j] = ljj;
+            D[j][j] = d * rs;
+            Dr[j] = rs;
             if (bad && blockIdx.x == 0) atomicCAS(info, 0, k0 + j + 1);
           } else if (t > j) {
-            D[t][j] = D[t][j] / ljj;
+            D[t][j] = D[t][j] * rs;
           }
         }
         __syncthreads();
@@ -312,7 +314,7 @@ chol_fused_kernel(const double* __restrict__ G, const double* __restrict__ Gbc, 
           double sacc = x[j];
 #pragma unroll
           for (int mm = 0; mm < j; ++mm) sacc = fma(-x[mm], D[j][mm], sacc);
-          x[j] = sacc / D[j][j];
+          x[j] = sacc * Dr[j];
         }
 #pragma unroll
         for (int j = 0; j < CB; ++j) __stcg(row + j, x[j]);

@@ -202,7 +202,7 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   FPS_CUDA(cudaMalloc(&ctx->tc_sched, 2 * sizeof(int)));
   FPS_CUDA(cudaMemset(ctx->tc_sched, 0, 2 * sizeof(int)));
   ctx->workspace_bytes = 4 * plane + ctx->partial_bytes;
-  if (tc_init(ctx) || chol_init(ctx)) { fps_destroy(ctx); return 3; }
+  if (tc_init(ctx) || chol_init(ctx) || sources_init(ctx)) { fps_destroy(ctx); return 3; }
   *out = ctx;
   return 0;
 }
@@ -360,13 +360,17 @@ int fps_get_scales(const fps_ctx* ctx, float* out24) {
   return 0;
 }
 
-int fps_set_scales(fps_ctx* ctx, const float* in24) {
-  FPS_REQUIRE(ctx && in24, "fps_set_scales: null argument");
+int fps_set_calibration(fps_ctx* ctx, const float* in24, int gain_on) {
+  FPS_REQUIRE(ctx && in24, "fps_set_calibration: null argument");
   for (int l = 0; l < NLAYER; ++l)
     for (int s = 0; s < 4; ++s) {
-      FPS_REQUIRE(in24[4 * l + s] > 0.f && in24[4 * l + s] < 1.0e30f, "fps_set_scales: scale %d is not positive", 4 * l + s);
+      FPS_REQUIRE(in24[4 * l + s] > 0.f && in24[4 * l + s] < 1.0e30f, "fps_set_calibration: scale %d is not positive", 4 * l + s);
       ctx->act_scale[l].s[s] = in24[4 * l + s];
     }
+  if (gain_on >= 0) {
+    ctx->gain_off = gain_on ? 0 : 1;
+    ctx->gain_checked = 1;
+  }
   return 0;
 }
 

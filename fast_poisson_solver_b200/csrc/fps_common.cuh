@@ -151,6 +151,7 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
                     bool last, float* H, float* DH, int64_t ld, const FusedOut* fused, cudaStream_t st);
 int tc_init(fps_ctx* ctx);
 int chol_init(fps_ctx* ctx);
+int sources_init(fps_ctx* ctx);
 void tc_destroy(fps_ctx* ctx);
 
 // C (M x Ncols, ldc) fp64 += A^T B over n rows; A (n, lda) fp32 M columns, B (n, ldb) fp32 Ncols columns.
@@ -249,6 +250,23 @@ __device__ __forceinline__ void store_planes_t(const ActPlanes& P, size_t idx, f
 __device__ __forceinline__ float load_planes(const ActPlanes& P, size_t idx, float inv_scale) {
   if (P.f16) return (__half2float(P.hi16[idx]) + __half2float(P.lo16[idx])) * inv_scale;
   return P.hi[idx] + P.lo[idx];
+}
+
+// Balanced radix-256 digits of a 31-bit integer X = d0 2^24 + d1 2^16 + d2 2^8 + d3 with d1..d3 in [-128, 127]
+// (|X| <= 2^30, so |d0| <= 64), all four at once: adding 128 at the three lower byte positions turns every balanced
+// digit into its offset-binary byte, and flipping those sign bits back gives the two's complement bytes
+// [d0 | d1 | d2 | d3] (d0 in the top byte).
+__device__ __forceinline__ uint32_t balanced_digits4(int X) {
+  return ((uint32_t)X + 0x00808080u) ^ 0x00808080u;
+}
+// 4 x 4 byte transpose: z[u] = digits word of element u -> w[s] = digit s of the elements 0..3 (element 0 in the low byte)
+__device__ __forceinline__ void digits_transpose4(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3, uint32_t* w) {
+  const uint32_t t0 = __byte_perm(z0, z1, 0x5140), t1 = __byte_perm(z0, z1, 0x7362);
+  const uint32_t t2 = __byte_perm(z2, z3, 0x5140), t3 = __byte_perm(z2, z3, 0x7362);
+  w[3] = __byte_perm(t0, t2, 0x5410);
+  w[2] = __byte_perm(t0, t2, 0x7632);
+  w[1] = __byte_perm(t1, t3, 0x5410);
+  w[0] = __byte_perm(t1, t3, 0x7632);
 }
 
 __device__ __forceinline__ void split_store(float* hi, float* lo, float v) {

@@ -96,23 +96,18 @@ gi_split_kernel(float* __restrict__ A, int64_t ld, int64_t n, int ncols, int row
   }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    uint32_t word[GI_SL] = {0u, 0u, 0u, 0u};
+    uint32_t word[GI_SL], z[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float v = vals[it * 4 + u];
-      int X = __float2int_rn(v * sc);
+      const int X = __float2int_rn(v * sc);
       if (SNAP) {
         const float snapped = (float)X * inv_sc;   // exact: X has at most 24 significant bits
         if (snapped != v) A[(pbase + it * 4 + u) * ld + f] = snapped;
       }
-#pragma unroll
-      for (int s = GI_SL - 1; s >= 1; --s) {
-        const int d = ((X + 128) & 255) - 128;   // balanced digit in [-128, 127]
-        X = (X - d) >> 8;                         // exact
-        word[s] |= (uint32_t)(d & 255) << (8 * u);
-      }
-      word[0] |= (uint32_t)(X & 255) << (8 * u);  // |X| <= 64 here
+      z[u] = balanced_digits4(X);                  // |X| <= 2^30: [d0 | d1 | d2 | d3]
     }
+    digits_transpose4(z[0], z[1], z[2], z[3], word);
 #pragma unroll
     for (int s = 0; s < GI_SL; ++s) sm[s][fl][pq * 8 + it] = word[s];
   }

@@ -30,11 +30,12 @@
 // that compensates the first-order shrink, to a round-to-nearest fp32 running sum held in registers while the
 // tensor core already works on the next segment in the other TMEM buffer.
 //
-// Warp roles (320 threads, persistent CTAs, one per SM):
+// Warp roles (384 threads = 3 warpgroups, persistent CTAs, one per SM):
 //   warp 0     TMA producer (ring of {Ahi, Alo, Bhi, Blo} slabs: 3 stages x 64 KiB); in the pair leader also the
 //              tile scheduler (dynamic: a global ticket counter, see "tile sequence" below)
 //   warp 1     TMEM allocator + MMA issuer (one elected lane; in a pair only the rank-0 CTA issues)
-//   warps 2-9  accumulate + epilogue; TMEM lane quadrant = warp_id % 4, column half = (warp_id-2)/4,
+//   warps 2-3  idle (they complete the first warpgroup so that setmaxnreg can hand its registers to the others)
+//   warps 4-11 accumulate + epilogue; TMEM lane quadrant = warp_id % 4, column half = (warp_id-4)/4,
 //              128 running sums per thread.  The 512 TMEM columns hold two 256-column segment
 //              accumulators (double buffer between MMA issuer and accumulate warps).
 #include "fps_common.cuh"
@@ -50,7 +51,13 @@ constexpr int TN = 256;                 // activation rows per tile (UMMA N)
 constexpr int BOX_ROWS = 128;           // every TMA box is 128 rows x one swizzle span of K
 // The shared-memory row (= swizzle span = K bytes per slab) is a template parameter RB: 64 (SWIZZLE_64B,
 // 8 KiB boxes, 6-stage ring) or 128 (SWIZZLE_128B, 16 KiB boxes, full 128-byte L2 lines per TMA row).
-constexpr int TC_THREADS = 320;         // TMA warp, MMA warp, 8 accumulate/epilogue warps
+constexpr int TC_THREADS = 384;         // three warpgroups: {TMA warp, MMA warp, 2 idle warps}, 2 x 4 accumulate/epilogue warps
+// Register budget per warpgroup (setmaxnreg): the kernel launches with 168 registers per thread (65536 / 384); the
+// first warpgroup - two single-thread roles - shrinks to 64 and the 13312 registers it gives up let the eight
+// accumulate/epilogue warps grow to 216: their 128 running sums plus the epilogue's temporaries no longer spill
+// (ptxas: 0 bytes in the hidden-layer instance, 28 in the last-layer one; 40 / 232 made the control roles spill).
+constexpr int TC_REGS_CTRL = 64;
+constexpr int TC_REGS_EPI = 216;
 constexpr int TMEM_COLS = 512;
 constexpr int N_FEAT_TILES = FPW / TM;  // 6
 constexpr int RING_BYTES = 224 * 1024;
@@ -243,6 +250,10 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
     return t;
   };
 
+  if (warp < 4) {
+  // ---- first warpgroup: the two single-thread roles (every role's code is dominated by its own setmaxnreg, so that
+  // ptxas allocates each region with that region's budget)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -328,10 +339,12 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
         atomicAdd(&g_tc_stats[11], 1ull);
       }
     }
+  }
   } else {
-    // ================= accumulate + epilogue (warps 2..9) =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
+    // ================= accumulate + epilogue (warps 4..11) =================
     const int quad = warp % 4;          // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
-    const int half = (warp - 2) / 4;    // which 128 of the 256 accumulator columns
+    const int half = (warp - 4) / 4;    // which 128 of the 256 accumulator columns
     uint32_t abuf = 0, aphase = 0;
     for (;;) {
       const int t = next_tile_warp();
@@ -347,7 +360,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
         const long long t_c = clock64();
         mbar_wait(bar_tfull + 8 * abuf, aphase);
         const long long t_d = clock64();
-        if (warp == 2 && lane == 0) TC_STAT_ADD(3, t_d - t_c);
+        if (warp == 4 && lane == 0) TC_STAT_ADD(3, t_d - t_c);
         tc_fence_after();
         const uint32_t taddr = tmem_base + abuf * TN + half * (TN / 2) + ((uint32_t)(quad * 32) << 16);
         const float g = (kc0 + P.seg <= P.nk) ? P.gain : P.gain_tail;
@@ -364,7 +377,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           if (NCTA == 1) mbar_arrive(bar_tempty + 8 * abuf); else mbar_arrive_leader(bar_tempty + 8 * abuf);
         }
         if (++abuf == 2) { abuf = 0; aphase ^= 1; }
-        if (warp == 2 && lane == 0) TC_STAT_ADD(4, clock64() - t_d);
+        if (warp == 4 && lane == 0) TC_STAT_ADD(4, clock64() - t_d);
       }
       const long long t_e = clock64();
       // ---- epilogue: tanh recurrences, split into the next layer's operand planes, 128-byte coalesced stores
@@ -382,10 +395,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
         const bool planes = P.gplanes != nullptr;
         const float2 sd = (planes && f_ok) ? P.dh_scale[f] : make_float2(0.f, 0.f);
         uint32_t dg[4][8];
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4)
-#pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) dg[s4][w8] = 0u;
+        uint32_t zq[4] = {0u, 0u, 0u, 0u};
         float dh_max = 0.f;
         bool ovf = false;
 #pragma unroll
@@ -405,14 +415,13 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
             } else if (valid) {
               ovf = true;                                    // beyond the calibrated grid: keep dv, redo the split later
             }
-            if (!valid) X = 0;
+            zq[q & 3] = valid ? balanced_digits4(X) : 0u;
+            if ((q & 3) == 3) {
+              uint32_t w4[4];
+              digits_transpose4(zq[0], zq[1], zq[2], zq[3], w4);
 #pragma unroll
-            for (int s4 = 3; s4 >= 1; --s4) {
-              const int d = ((X + 128) & 255) - 128;         // balanced digit in [-128, 127]
-              X = (X - d) >> 8;
-              dg[s4][q >> 2] |= (uint32_t)(d & 255) << (8 * (q & 3));
+              for (int s4 = 0; s4 < 4; ++s4) dg[s4][q >> 2] = w4[s4];
             }
-            dg[0][q >> 2] |= (uint32_t)(X & 255) << (8 * (q & 3));
           }
           if (valid && f_ok) {
             const int64_t p = (r0 >> 2) + q;
@@ -456,7 +465,7 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
           }
         }
       }
-      if (warp == 2 && lane == 0) TC_STAT_ADD(5, clock64() - t_e);
+      if (warp == 4 && lane == 0) TC_STAT_ADD(5, clock64() - t_e);
     }
   }
 

@@ -51,20 +51,16 @@ ri_split_a_kernel(float* __restrict__ A, int64_t ld, int64_t n, int64_t n_pad, c
     float4 v = *reinterpret_cast<const float4*>(A + i * ld + k);
     float vv[4] = {v.x, v.y, v.z, v.w};
     bool changed = false;
+    uint32_t z[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float2 sc = scale[k + u];
-      int X = (k + u < F) ? __float2int_rn(vv[u] * sc.x) : 0;
+      const int X = (k + u < F) ? __float2int_rn(vv[u] * sc.x) : 0;
       const float snapped = (float)X * sc.y;
       if (snapped != vv[u]) { vv[u] = snapped; changed = true; }
-#pragma unroll
-      for (int s = RI_DA - 1; s >= 1; --s) {
-        const int d = ((X + 128) & 255) - 128;
-        X = (X - d) >> 8;
-        word[s] |= (uint32_t)(d & 255) << (8 * u);
-      }
-      word[0] |= (uint32_t)(X & 255) << (8 * u);
+      z[u] = balanced_digits4(X);
     }
+    digits_transpose4(z[0], z[1], z[2], z[3], word);
     if (changed) *reinterpret_cast<float4*>(A + i * ld + k) = make_float4(vv[0], vv[1], vv[2], vv[3]);
   }
 #pragma unroll

@@ -5,6 +5,7 @@
 // exist on the host (16M points x 4096 columns would be 275 GB).
 #include "fps_common.cuh"
 #include <algorithm>
+#include <math.h>
 
 namespace fps {
 
@@ -62,6 +63,10 @@ __device__ __forceinline__ uint32_t lattice_hash(int ix, int iy, uint32_t seed) 
   return h;
 }
 
+// 64 unit gradient directions, angle 2 pi k / 64 (filled once per context by sources_init: the same fp64 values as
+// numpy's cos / sin in sources.py); the top 6 bits of the lattice hash pick one
+__constant__ double c_grad[64][2];
+
 __device__ __forceinline__ double perlin_layer(double x, double y, double octave, uint32_t seed) {
   const double px = x * octave, py = y * octave;
   const double fx0 = floor(px), fy0 = floor(py);
@@ -74,9 +79,8 @@ __device__ __forceinline__ double perlin_layer(double x, double y, double octave
   for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
-      double sn, cs;
-      sincospi((double)lattice_hash(ix + dx, iy + dy, seed) * (2.0 / 4294967296.0), &sn, &cs);
-      n[dy][dx] = cs * (fx - dx) + sn * (fy - dy);
+      const uint32_t g = lattice_hash(ix + dx, iy + dy, seed) >> 26;
+      n[dy][dx] = c_grad[g][0] * (fx - dx) + c_grad[g][1] * (fy - dy);
     }
   return (n[0][0] * (1.0 - sx) + n[0][1] * sx) * (1.0 - sy) + (n[1][0] * (1.0 - sx) + n[1][1] * sx) * sy;
 }
@@ -102,6 +106,18 @@ perlin_sources_kernel(const double* __restrict__ x, const double* __restrict__ y
     if (q[16] != 0.0) u *= q[16] * perlin_layer(xv, yv, q[15], (uint32_t)q[17]);
     F[r * ldf + c0 + col] = (TO)u;
   }
+}
+
+int sources_init(fps_ctx* ctx) {
+  (void)ctx;
+  double g[64][2];
+  for (int k = 0; k < 64; ++k) {
+    const double a = 2.0 * 3.14159265358979323846 * (double)k / 64.0;
+    g[k][0] = cos(a);
+    g[k][1] = sin(a);
+  }
+  FPS_CUDA(cudaMemcpyToSymbol(c_grad, g, sizeof(g)));
+  return 0;
 }
 
 template <typename TO>

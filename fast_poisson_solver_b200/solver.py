@@ -34,7 +34,6 @@ Deliberate deviations from the reference:
 from __future__ import annotations
 
 import ctypes as C
-import hashlib
 import os
 import pickle
 import random
@@ -427,7 +426,7 @@ class Solver:
         _lib.check(self._lib.fps_get_scales(self._ctx, scales), "fps_get_scales")
         payload = {
             "format": _FORMAT, "dtype": str(self._fdtype), "FP": FP, "n": self._Hp.shape[0], "n_bc": self._Hbcp.shape[0],
-            "weights_sha256": self.weights_sha256, "act_scales": list(scales),
+            "weights_sha256": self.weights_sha256, "act_scales": list(scales), "gain_on": self._gain_on(),
             "H": self._Hp.cpu(), "DH": self._DHp.cpu(), "H_bc": self._Hbcp.cpu(), "pack": self._pack.cpu(),
             "xop_h": None if self._xop_h is None else self._xop_h.cpu(),
             "xop_dh": None if self._xop_dh is None else self._xop_dh.cpu(),
@@ -437,6 +436,11 @@ class Solver:
             pickle.dump(payload, fh, protocol=pickle.HIGHEST_PROTOCOL)
         if self.verbose > 0:
             print("Pre-Computed stored.")
+
+    def _gain_on(self):
+        cal = (C.c_double * 5)()
+        _lib.check(self._lib.fps_get_calibration(self._ctx, cal), "fps_get_calibration")
+        return int(cal[4])
 
     def _load_precomputed(self, n_loc, nbc_loc):
         """Returns False (-> recompute, as the reference does for a missing file) when the file does not describe this
@@ -469,7 +473,7 @@ class Solver:
         self._gplanes = self._rplanes_h = self._rplanes_dh = None   # rebuilt on demand from the stored (snapped) matrices
         # the operand scales the stored H was produced with (evaluate() must reproduce the same features)
         sc = (C.c_float * 24)(*p["act_scales"])
-        _lib.check(self._lib.fps_set_scales(self._ctx, sc), "fps_set_scales")
+        _lib.check(self._lib.fps_set_calibration(self._ctx, sc, int(p.get("gain_on", -1))), "fps_set_calibration")
         self._refactor_pending = False
         if list(p["lambdas"]) == list(self.lambdas_pde):
             self._L64, self.jitter = p["L64"].to(self._tdev), p["jitter"]
@@ -508,7 +512,7 @@ class Solver:
     def _ensure_recon_planes(self):
         """Feature-major digit planes of H and DH for the batched reconstruction: built once per precompute, on the
         first batched solve (a pure cache: H and DH already lie on their grids, nothing is modified)."""
-        if self._rplanes_h is not None or self._xop_h is None or self._rplanes_h is False:
+        if self._rplanes_h is not None or self._xop_h is None:
             return
         n_loc = self._DHp.shape[0]
         nbytes = int(self._lib.fps_recon_planes_bytes(n_loc))
@@ -647,7 +651,7 @@ class Solver:
         n_loc, nbc_loc = self._DHp.shape[0], self._Hbcp.shape[0]
         lib, ctx = self._lib, self._ctx
         if n_loc:
-            if exact and self._rplanes_h not in (None, False):
+            if exact and isinstance(self._rplanes_h, torch.Tensor):
                 _lib.check(lib.fps_reconstruct_x(ctx, self._xop_h.data_ptr(), self._rplanes_h.data_ptr(), n_loc, W.data_ptr(),
                                                  B, bias.data_ptr(), B, U.data_ptr(), B, st), "fps_reconstruct_x(u_pde)")
                 _lib.check(lib.fps_reconstruct_x(ctx, self._xop_dh.data_ptr(), self._rplanes_dh.data_ptr(), n_loc,

@@ -58,8 +58,8 @@ def sine_sources(solver, params, x=None, y=None, out=None) -> torch.Tensor:
 # ~ U(-100,100), one integer seed per layer) and, with probability 0.7, multiplies the sum by one more layer
 # (octaves ~ U(0.1,3), amplitude ~ U(-1,1)).  That package is a per-point Python loop and is absent here; sources are
 # INPUTS to the path, so the generator below keeps the family (same parameter draws, same quintic fade, same
-# lattice-gradient construction, coordinates scaled by `octaves`) but draws its lattice gradients from an integer
-# hash, which the device kernel (csrc/sources.cu: perlin_sources_kernel) evaluates identically.
+# lattice-gradient construction, coordinates scaled by `octaves`) but picks its lattice gradients (64 unit directions)
+# with an integer hash, which the device kernel (csrc/sources.cu: perlin_sources_kernel) evaluates identically.
 PERLIN_LAYERS = 5          # rows 0..4 of a parameter block: additive layers {octave, amplitude, seed}
 PERLIN_ROWS = 6            # row 5: multiplicative modulation layer (amplitude 0 = none)
 
@@ -77,6 +77,9 @@ def perlin_params(B: int, seed: int = 0) -> np.ndarray:
         if rng.random() > 0.3:
             p[j, 5] = (rng.uniform(0.1, 3.0), rng.uniform(-1.0, 1.0), rng.integers(1, 1000000))
     return p
+
+
+_GRAD = np.stack([np.cos(2.0 * np.pi * np.arange(64) / 64.0), np.sin(2.0 * np.pi * np.arange(64) / 64.0)], axis=1)
 
 
 def _lattice_hash(ix, iy, seed):
@@ -101,8 +104,8 @@ def _perlin_layer(x, y, octave, seed):
     sy = fy * fy * fy * (fy * (fy * 6.0 - 15.0) + 10.0)
 
     def corner(dx, dy):
-        ang = _lattice_hash(ix + dx, iy + dy, int(seed)).astype(np.float64) * (2.0 * np.pi / 4294967296.0)
-        return np.cos(ang) * (fx - dx) + np.sin(ang) * (fy - dy)
+        g = (_lattice_hash(ix + dx, iy + dy, int(seed)) >> np.uint32(26)).astype(np.int64)   # one of 64 directions
+        return _GRAD[g, 0] * (fx - dx) + _GRAD[g, 1] * (fy - dy)
 
     n00, n10, n01, n11 = corner(0, 0), corner(1, 0), corner(0, 1), corner(1, 1)
     return (n00 * (1.0 - sx) + n10 * sx) * (1.0 - sy) + (n01 * (1.0 - sx) + n11 * sx) * sy
@@ -123,3 +126,37 @@ def perlin_sources_numpy(x, y, params) -> np.ndarray:
             u *= amp * _perlin_layer(x, y, octave, seed)
         out[:, j] = u
     return out
+
+
+def perlin_sources(solver, params, x=None, y=None, out=None) -> torch.Tensor:
+    """Evaluate B Perlin-family sources on the solver's PDE points (or on given device float64 coordinates) on the
+    device (csrc/sources.cu: perlin_sources_kernel); (n, B) in the solver's feature dtype."""
+    dev = solver._tdev
+    x64 = solver._xy64[0] if x is None else x
+    y64 = solver._xy64[1] if y is None else y
+    n, B = x64.numel(), params.shape[0]
+    assert params.shape[1:] == (PERLIN_ROWS, 3)
+    pd = torch.as_tensor(np.ascontiguousarray(params), dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty((n, B), dtype=solver._fdtype, device=dev)
+    fn = solver._lib.fps_perlin_sources_f64 if out.dtype == torch.float64 else solver._lib.fps_perlin_sources
+    _lib.check(fn(solver._ctx, x64.data_ptr(), y64.data_ptr(), n, pd.data_ptr(), B, out.data_ptr(), out.stride(0),
+                  solver._stream()), "fps_perlin_sources")
+    return out
+
+
+def grid_points(solver, G: int, rank: int = 0, world: int = 1):
+    """Device float64 coordinates of the reference generator's geometry (data.py:192-217): this rank's block of the
+    G x G interior grid and of the 4G + 4 boundary ring (block sharding as parallel.shard_bounds)."""
+    from .parallel import shard_bounds
+
+    dev = solver._tdev
+    lo, hi = shard_bounds(G * G, rank, world)
+    blo, bhi = shard_bounds(4 * G + 4, rank, world)
+    x = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    y = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    xb = torch.empty(bhi - blo, dtype=torch.float64, device=dev)
+    yb = torch.empty(bhi - blo, dtype=torch.float64, device=dev)
+    _lib.check(solver._lib.fps_grid_points(solver._ctx, G, lo, hi - lo, x.data_ptr(), y.data_ptr(), blo, bhi - blo,
+                                           xb.data_ptr(), yb.data_ptr(), solver._stream()), "fps_grid_points")
+    return x, y, xb, yb

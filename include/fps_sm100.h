@@ -75,8 +75,9 @@ int fps_set_engine(fps_ctx* ctx, int engine);
  * fps_get_scales copies the 6 x 4 scales out (host float[24]).                                       */
 int fps_calibrate_scales(fps_ctx* ctx, const double* x, const double* y, int64_t n, void* stream);
 int fps_get_scales(const fps_ctx* ctx, float* h_out24);
-/* Restore scales taken with fps_get_scales (a saved precompute state must be evaluated with the scales it was built with). */
-int fps_set_scales(fps_ctx* ctx, const float* h_in24);
+/* Restore a calibration (a saved precompute state must be evaluated with the operand scales and the compensation
+ * setting it was built with): scales from fps_get_scales, gain_on = element 4 of fps_get_calibration (-1: leave).    */
+int fps_set_calibration(fps_ctx* ctx, const float* h_in24, int gain_on);
 /* The same call (a) records max |DH| per feature over the sample, from which fps_features_x derives the fixed-point grid
  * of its fused digit split, and (b) once per context checks the tensor-core kernel's accumulator-gain compensation
  * (csrc/layer_tc.cu) against the fp32 FFMA engine on the sample, switching it off for weight sets where it hurts.

@@ -114,3 +114,29 @@ def test_format_input_contract():
     assert e.shape == (2, 3) and e.dtype == torch.float64
     (f,) = format_input([[1.0, 2.0]], as_array=True)
     assert isinstance(f, np.ndarray) and f.shape == (2, 1)
+
+
+def test_perlin_family_host_generator():
+    """Host mirror of the device Perlin generator: deterministic, smooth across lattice cells, parameter draws in the
+    ranges of source_functions.py:173-227."""
+    from fast_poisson_solver_b200.sources import perlin_params, perlin_sources_numpy
+
+    p = perlin_params(64, seed=1)
+    assert p.shape == (64, 6, 3)
+    used = p[:, :5, 1] != 0
+    assert used.sum(1).min() >= 1 and used.sum(1).max() <= 5
+    assert p[:, :5, 0][used].min() >= 0.1 and p[:, :5, 0][used].max() <= 12 and np.abs(p[:, :5, 1]).max() <= 100
+    assert 0.5 < (p[:, 5, 1] != 0).mean() < 0.9          # the modulation layer is applied with probability 0.7
+    x = np.linspace(0, 1, 2001)
+    F = perlin_sources_numpy(x, np.full_like(x, 0.37), p[:4])
+    assert np.array_equal(F, perlin_sources_numpy(x, np.full_like(x, 0.37), p[:4]))
+    assert np.isfinite(F).all() and np.abs(F).max() > 0.1
+    assert np.abs(np.diff(F, axis=0)).max() < 0.05 * np.abs(F).max() + 1.0   # continuous (quintic fade)
+
+
+def test_shard_bounds_cover_everything():
+    from fast_poisson_solver_b200.parallel import shard_bounds
+
+    for n, w in ((10, 3), (4100, 8), (7, 8), (1 << 20, 4)):
+        b = [shard_bounds(n, r, w) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))

@@ -106,3 +106,49 @@ def test_fd_oracle_dst_equals_sparse_lu_restatement():
         exact = 3 - 50 / (13 * np.pi ** 2) * np.sin(2 * np.pi * x) * np.sin(3 * np.pi * y)
         errs.append(o.rel_l2(fd.fd_solve_dst(g, 50 * np.sin(2 * np.pi * x) * np.sin(3 * np.pi * y), 3.0), exact))
     assert 3.0 < errs[0] / errs[1] < 4.5
+
+
+@pytest.mark.parametrize("name", ["sources_G32_seed0.npz", "sources_G100_seed0.npz"])
+def test_oracle_vs_reference_on_baseline_source_families(golden, weights0, name):
+    """BASELINE's own source families (six draws of the reference's sincos 'random' family, four Perlin-family fields)
+    through the unmodified reference in fp64 (oracle/make_golden.py sources): the oracle reproduces u to the fp64
+    reference's own reproducibility on this cond ~1e15 system, orders of magnitude below the reference's fp32 run."""
+    import os
+    from conftest import GOLDEN
+
+    if not os.path.exists(os.path.join(GOLDEN, name)):
+        pytest.skip(f"{name} not minted")
+    g = golden(name)
+    xp, yp, xb, yb = o.grid_problem(int(g["G"]))
+    st = o.precompute(xp, yp, xb, yb, weights0, dtype=np.float64)
+    for j, nm in enumerate(g["names"]):
+        u = o.solve(st, g["F"][:, j], np.full_like(xb, g["bc"][j]))[0]
+        e = o.rel_l2(u, g["U_f64"][:, [j]])
+        floor = o.rel_l2(g["U_f32"][:, [j]], g["U_f64"][:, [j]])
+        assert e < 1e-5 and e < 0.05 * floor, (str(nm), e, floor)
+
+
+def test_fd_oracle_vs_reference_numeric_solve(golden):
+    """oracle/fd_oracle.py against the reference's OWN numeric_solve (numeric_solver.py:39-160, run through
+    oracle/make_golden.py numeric): sparse-LU restatement and exact DST agree with it to solver rounding."""
+    from oracle import fd_oracle as fd
+
+    g = golden("numeric_solve_seed0.npz")
+    for G in (48, 200):
+        xp, yp, xb, yb = o.grid_problem(G)
+        for tag in ("sine", "smooth"):
+            f, bcv, u_ref = g[f"f_G{G}_{tag}"], float(g[f"bc_G{G}_{tag}"]), g[f"u_G{G}_{tag}"]
+            assert u_ref.shape == (G * G + 4 * G + 4,)
+            u = fd.fd_solve_dst(G, f, bcv)
+            assert o.rel_l2(u, u_ref[: G * G]) < 1e-10, (G, tag)
+            assert np.all(u_ref[G * G:] == bcv)
+            if G == 48:
+                assert o.rel_l2(fd.fd_solve_sparse(G, f, bcv), u_ref[: G * G]) < 1e-10
+    # G = 400 (the README's 5 s case): analytic source, u stored at stride 7
+    G = 400
+    xp, yp, _, _ = o.grid_problem(G)
+    f = 50.0 * np.sin(2 * np.pi * xp) * np.sin(3 * np.pi * yp)
+    u = np.concatenate([fd.fd_solve_dst(G, f, 3.0), np.full(4 * G + 4, 3.0)])
+    assert o.rel_l2(u[::7], g["u_G400_smooth"]) < 1e-9
+    u = np.concatenate([fd.fd_solve_dst(G, o.sine_source(xp, yp, seed=G), -2.5), np.full(4 * G + 4, -2.5)])
+    assert o.rel_l2(u[::7], g["u_G400_sine"]) < 1e-9
