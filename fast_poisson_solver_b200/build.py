@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfps_sm100.so")
-SOURCES = ["fps_api.cu", "fourier.cu", "layer_simt.cu", "layer_tc.cu", "features_f64.cu", "gemm_f64.cu", "gram_i8.cu", "recon_i8.cu", "xop.cu", "chol.cu", "sources.cu", "fd_dst.cu"]
+SOURCES = ["fps_api.cu", "fourier.cu", "layer_simt.cu", "layer_tc.cu", "features_f64.cu", "gemm_f64.cu", "gram_i8.cu", "recon_i8.cu", "xop.cu", "stream_f32.cu", "chol.cu", "sources.cu", "fd_dst.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
-        r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+        r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB

@@ -23,183 +23,6 @@ constexpr int CN = FP;   // matrix order incl. padding
 constexpr int CB = 32;   // panel width
 constexpr int CNB = CN / CB;  // 22 panels
 
-// ---- assemble ----------------------------------------------------------------------------------
-// counts != null: {N, N_bc} are read from device memory (the all-reduced packed buffer) and lam_over_n holds lambda
-__global__ void assemble_kernel(const double* __restrict__ G, const double* __restrict__ Gbc,
-                                const double* __restrict__ s, double lam_over_n, double inv_nbc, double jitter,
-                                const double* __restrict__ counts, double* __restrict__ L) {
-  const int i = blockIdx.x;
-  if (counts) {
-    lam_over_n = lam_over_n / counts[0];
-    inv_nbc = 1.0 / counts[1];
-  }
-  for (int j = threadIdx.x; j < CN; j += blockDim.x) {
-    double v;
-    if (i < F && j < F) {
-      v = lam_over_n * G[(size_t)i * CN + j] + (Gbc[(size_t)i * CN + j] - s[i] * s[j] * inv_nbc) * inv_nbc;
-      if (i == j) v += jitter;
-    } else {
-      v = (i == j) ? 1.0 : 0.0;
-    }
-    L[(size_t)i * CN + j] = v;
-  }
-}
-
-// max diagonal of the assembled matrix (first F entries) -> scal[0]; resets info.
-__global__ void diagmax_kernel(const double* __restrict__ L, double* __restrict__ scal, int* __restrict__ info) {
-  __shared__ double red[32];
-  double m = 0.0;
-  for (int i = threadIdx.x; i < F; i += blockDim.x) m = fmax(m, L[(size_t)i * CN + i]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)blockDim.x / 32; ++w) m = fmax(m, red[w]);
-    scal[0] = m;
-    *info = 0;
-  }
-}
-
-// ---- panel: factor the 32x32 diagonal block (every CTA, redundantly) and solve the rows below ----
-// L21 = A21 * L11^-T.  The factored diagonal block goes to Dfac (CTA 0 only) so that CTAs that are
-// still reading the unfactored block from L never race with the write-back; fixup_kernel installs
-// the diagonal blocks at the end.
-__global__ void __launch_bounds__(256)
-chol_panel_kernel(double* __restrict__ L, int kb, double* __restrict__ Dfac, const double* __restrict__ scal,
-                  int* __restrict__ info) {
-  __shared__ double D[CB][CB + 1];
-  const int k0 = kb * CB;
-  const int t = threadIdx.x;
-  for (int e = t; e < CB * CB; e += 256) D[e / CB][e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
-  const double tol = DBL_EPSILON * scal[0];
-  const double safe = scal[0] > 0.0 ? scal[0] : 1.0;
-  for (int j = 0; j < CB; ++j) {
-    __syncthreads();
-    double d = D[j][j];
-    const bool bad = !(d > tol);
-    if (bad) d = safe;  // keep the arithmetic finite; the host sees info != 0 and retries with a shift
-    const double ljj = sqrt(d);
-    __syncthreads();
-    if (t < CB) {
-      if (t == j) {
-        D[j][j] = ljj;
-        if (bad && blockIdx.x == 0) atomicCAS(info, 0, k0 + j + 1);
-      } else if (t > j) {
-        D[t][j] = D[t][j] / ljj;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = t + 256 * q;
-      const int i = e / CB, m = e % CB;
-      if (m > j && i >= m) D[i][m] -= D[i][j] * D[m][j];
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0)
-    for (int e = t; e < CB * CB; e += 256) Dfac[(size_t)kb * CB * CB + e] = (e % CB <= e / CB) ? D[e / CB][e % CB] : 0.0;
-
-  const int r = k0 + CB + blockIdx.x * 256 + t;
-  if (r < CN) {
-    double x[CB];
-    double* row = L + (size_t)r * CN + k0;
-#pragma unroll
-    for (int j = 0; j < CB; ++j) x[j] = row[j];
-#pragma unroll
-    for (int j = 0; j < CB; ++j) {
-      double sacc = x[j];
-#pragma unroll
-      for (int m = 0; m < j; ++m) sacc = fma(-x[m], D[j][m], sacc);
-      x[j] = sacc / D[j][j];
-    }
-#pragma unroll
-    for (int j = 0; j < CB; ++j) row[j] = x[j];
-  }
-}
-
-// ---- trailing update: A22 -= L21 L21^T on lower-triangular 64x64 tiles -----------------------------
-__global__ void __launch_bounds__(256)
-chol_update_kernel(double* __restrict__ L, int kb) {
-  __shared__ double Pi[64][CB + 1];
-  __shared__ double Pj[64][CB + 1];
-  const int base = (kb + 1) * CB;
-  int tile = blockIdx.x, ti, tj;
-  ti = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
-  while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-  while (ti * (ti + 1) / 2 > tile) --ti;
-  tj = tile - ti * (ti + 1) / 2;
-  const int i0 = base + ti * 64, j0 = base + tj * 64;
-  const int k0 = kb * CB;
-  for (int e = threadIdx.x; e < 64 * CB; e += 256) {
-    const int r = e / CB, c = e % CB;
-    Pi[r][c] = (i0 + r < CN) ? L[(size_t)(i0 + r) * CN + k0 + c] : 0.0;
-    Pj[r][c] = (j0 + r < CN) ? L[(size_t)(j0 + r) * CN + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < CB; ++k) {
-    double pa[4], pb[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) pa[a] = Pi[ty + 16 * a][k];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) pb[b] = Pj[tx + 16 * b][k];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fma(pa[a], pb[b], acc[a][b]);
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-      if (i < CN && j <= i) L[(size_t)i * CN + j] -= acc[a][b];
-    }
-}
-
-// ---- fixup: install factored diagonal blocks, mirror L into the upper triangle (so that both
-// triangular sweeps read rows contiguously) --------------------------------------------------------
-__global__ void chol_fixup_kernel(double* __restrict__ L, const double* __restrict__ Dfac) {
-  const int i = blockIdx.x;
-  const int kb = i / CB;
-  for (int j = threadIdx.x; j <= i; j += blockDim.x) {
-    double v;
-    if (j >= kb * CB) v = Dfac[(size_t)kb * CB * CB + (i - kb * CB) * CB + (j - kb * CB)];
-    else v = L[(size_t)i * CN + j];
-    L[(size_t)i * CN + j] = v;
-    if (j < i) L[(size_t)j * CN + i] = v;
-  }
-}
-
-// Inverses of the 22 diagonal 32x32 blocks of L, stored in rows 704..735 of the factor buffer (block kb in
-// columns 32 kb .. 32 kb + 31).  The batched solve applies them as small mat-vecs instead of 32 sequential
-// substitution steps; one step of iterative refinement against the block itself keeps the block solve
-// backward stable.  One warp per block, lane j builds column j by forward substitution on e_j.
-__global__ void chol_dinv_kernel(double* __restrict__ L) {
-  __shared__ double D[CB][CB + 1];
-  const int kb = blockIdx.x, k0 = kb * CB, j = threadIdx.x;
-  for (int e = threadIdx.x; e < CB * CB; e += 32) D[e / CB][e % CB] = L[(size_t)(k0 + e / CB) * CN + k0 + e % CB];
-  __syncwarp();
-  double x[CB];
-#pragma unroll
-  for (int i = 0; i < CB; ++i) {
-    double sacc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int m = 0; m < i; ++m) sacc = fma(-D[i][m], x[m], sacc);
-    x[i] = (i >= j) ? sacc / D[i][i] : 0.0;
-  }
-#pragma unroll
-  for (int i = 0; i < CB; ++i) L[(size_t)(CN + i) * CN + k0 + j] = x[i];
-}
-
 // ---- the whole factorisation in ONE launch -------------------------------------------------------------------------
 // assemble -> max diagonal -> 22 x (panel, trailing update) -> fixup + diagonal-block inverses, with a grid-wide barrier
 // between the phases instead of 48 kernel launches (the 704 x 704 problem is 0.11 GFLOP: pure latency).  CF_CTAS CTAs,
@@ -382,7 +205,9 @@ chol_fused_kernel(const double* __restrict__ G, const double* __restrict__ Gbc, 
       if (j < i) __stcg(L + (size_t)j * CN + i, v);
     }
   }
-  // ---- inverses of the diagonal blocks (rows 704..735 of the factor buffer), one warp per block, from Dfac
+  // ---- inverses of the diagonal blocks (rows 704..735 of the factor buffer), one warp per block, from Dfac; they also
+  // seed the diagonal of the explicit inverse below
+  double* Xf = L + (size_t)(CN + CB) * CN;   // (CN x CN): lower triangle X = L^-1, upper triangle X^T
   for (int kb = blockIdx.x; kb < CNB; kb += gridDim.x) {
     __syncthreads();
     for (int e = t; e < CB * CB; e += 256) D[e / CB][e % CB] = __ldcg(Dfac + (size_t)kb * CB * CB + e);
@@ -398,9 +223,107 @@ chol_fused_kernel(const double* __restrict__ G, const double* __restrict__ Gbc, 
         x[i] = (i >= j) ? sacc / D[i][i] : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < CB; ++i) L[(size_t)(CN + i) * CN + kb * CB + j] = x[i];
+      for (int i = 0; i < CB; ++i) {
+        L[(size_t)(CN + i) * CN + kb * CB + j] = x[i];
+        __stcg(Xf + (size_t)(kb * CB + i) * CN + kb * CB + j, x[i]);
+      }
     }
   }
+  // ---- explicit inverse X = L^-1 (applied by the few-right-hand-side solve as GEMVs with one refinement step against
+  // L itself, instead of 44 dependent substitution steps).  Recursive merging of diagonal segments: for a pair of
+  // adjacent segments [a0, a1), [a1, a2) whose inverses X11, X22 are known,
+  //     X21 = -X22 (L21 X11)
+  // - two rounds of independent 64 x 64 tile products per level, five levels for the 22 blocks (22 -> 11 -> 6 -> 3 -> 2
+  // -> 1 segments).  T = L21 X11 is parked transposed in the (still unused) upper triangle of Xf.
+  __shared__ int segb[CNB + 1];
+  int nseg = CNB;
+  if (t <= CNB) segb[t] = t * CB;
+  cf_grid_barrier(bar, target);
+  while (nseg > 1) {
+    const int npair = nseg / 2;
+    for (int phase = 0; phase < 2; ++phase) {
+      // tiles of all pairs of this level, dealt round-robin to the CTAs
+      int tile = blockIdx.x;
+      for (int p = 0; p < npair; ++p) {
+        const int a0 = segb[2 * p], a1 = segb[2 * p + 1], a2 = segb[2 * p + 2];
+        const int tr = (a2 - a1 + 63) / 64, tc = (a1 - a0 + 63) / 64;
+        for (; tile < tr * tc; tile += gridDim.x) {
+          const int r0 = a1 + (tile / tc) * 64, c0 = a0 + (tile % tc) * 64;
+          // phase 0: T[r][c] = sum_{k = c .. a1-1} L[r][k] X11[k][c]      (X11 lower triangular)
+          // phase 1: X21[r][c] = - sum_{k = a1 .. r} X22[r][k] T[k][c]    (X22 lower triangular; T read from the mirror)
+          const int kbeg = phase == 0 ? (c0 / CB) * CB : a1;
+          const int kend = phase == 0 ? a1 : min(a2, r0 + 64);
+          const int tx = t % 16, ty = t / 16;
+          double acc[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+          for (int k0 = kbeg; k0 < kend; k0 += CB) {
+            __syncthreads();
+            for (int e = t; e < 64 * CB; e += 256) {
+              const int rr = e / CB, kk = e % CB;          // Pi[row][k]: the left operand, read along k
+              const int r = r0 + rr, k = k0 + kk;
+              double v = 0.0;
+              if (r < a2 && k < kend) {
+                if (phase == 0) v = __ldcg(L + (size_t)r * CN + k);
+                else if (k <= r) v = __ldcg(Xf + (size_t)r * CN + k);
+              }
+              Pi[rr][kk] = v;
+            }
+            for (int e = t; e < 64 * CB; e += 256) {
+              // Pj[col][k]: the right operand; phase 0 reads rows of X11 (columns contiguous), phase 1 rows of T^T (k contiguous)
+              const int kk = phase == 0 ? e / 64 : e % CB, cc = phase == 0 ? e % 64 : e / CB;
+              const int c = c0 + cc, k = k0 + kk;
+              double v = 0.0;
+              if (c < a1 && k < kend) {
+                if (phase == 0) { if (k >= c) v = __ldcg(Xf + (size_t)k * CN + c); }
+                else v = __ldcg(Xf + (size_t)c * CN + k);    // T[k][c], stored transposed
+              }
+              Pj[cc][kk] = v;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int k = 0; k < CB; ++k) {
+              double pa[4], pb[4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) pa[a] = Pi[ty + 16 * a][k];
+#pragma unroll
+              for (int b = 0; b < 4; ++b) pb[b] = Pj[tx + 16 * b][k];
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(pa[a], pb[b], acc[a][b]);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int r = r0 + ty + 16 * a, c = c0 + tx + 16 * b;
+              if (r < a2 && c < a1) {
+                if (phase == 0) __stcg(Xf + (size_t)c * CN + r, acc[a][b]);
+                else __stcg(Xf + (size_t)r * CN + c, -acc[a][b]);
+              }
+            }
+        }
+        tile -= tr * tc;
+      }
+      cf_grid_barrier(bar, target);
+    }
+    // next level: every pair becomes one segment, an odd last segment is carried over
+    __syncthreads();
+    const int nnew = npair + (nseg & 1);
+    int keep = 0;
+    if (t <= nnew) keep = (t < npair) ? segb[2 * t] : (t == nnew ? CN : segb[2 * npair]);
+    __syncthreads();
+    if (t <= nnew) segb[t] = keep;
+    __syncthreads();
+    nseg = nnew;
+  }
+  // ---- mirror: upper triangle of Xf = X^T (the transposed products of the backward sweep read rows, too)
+  for (int i = blockIdx.x; i < CN; i += gridDim.x)
+    for (int j = t; j < i; j += 256) __stcg(Xf + (size_t)j * CN + i, __ldcg(Xf + (size_t)i * CN + j));
 }
 
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
@@ -411,41 +334,20 @@ int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gb
   // scratch in the partial workspace: [0] = max diag, then the 22 factored diagonal blocks
   double* scal = ctx->partial;
   double* Dfac = ctx->partial + 8;
-  static const int fused_env = getenv("FPS_CHOL_FUSED") ? atoi(getenv("FPS_CHOL_FUSED")) : 1;
-  if (fused_env && ctx->sm_count >= CF_CTAS) {
-    for (int li = 0; li < n_lambda; ++li) {
-      double* Ll = L + (size_t)li * FPS_LROWS * CN;
-      // scal[0] = max diagonal (as ordered bits), scal[1] = barrier counter
-      FPS_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(double), st));
-      chol_fused_kernel<<<CF_CTAS, 256, 0, st>>>(G, Gbc, s, h_lambdas[li], (double)n_total, (double)nbc_total, d_counts,
-                                                 h_jitter ? h_jitter[li] : 0.0, Ll, Dfac,
-                                                 reinterpret_cast<unsigned long long*>(scal),
-                                                 reinterpret_cast<unsigned*>(scal + 1), info + li);
-    }
-    count_launch(n_lambda);
-    FPS_CUDA(cudaGetLastError());
-    return 0;
-  }
+  FPS_REQUIRE(ctx->sm_count >= CF_CTAS, "assemble_factor: %d SMs < %d co-resident CTAs", ctx->sm_count, CF_CTAS);
   for (int li = 0; li < n_lambda; ++li) {
     double* Ll = L + (size_t)li * FPS_LROWS * CN;
-    const double lam = h_lambdas[li];
-    const double jitter = h_jitter ? h_jitter[li] : 0.0;
-    if (d_counts) assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam, 0.0, jitter, d_counts, Ll);
-    else assemble_kernel<<<CN, 256, 0, st>>>(G, Gbc, s, lam / (double)n_total, 1.0 / (double)nbc_total, jitter, nullptr, Ll);
-    diagmax_kernel<<<1, 256, 0, st>>>(Ll, scal, info + li);
-    for (int kb = 0; kb < CNB; ++kb) {
-      const int below = CN - (kb + 1) * CB;
-      const int pc = below > 0 ? (below + 255) / 256 : 1;
-      chol_panel_kernel<<<pc, 256, 0, st>>>(Ll, kb, Dfac, scal, info + li);
-      if (below > 0) {
-        const int t64 = (below + 63) / 64;
-        chol_update_kernel<<<t64 * (t64 + 1) / 2, 256, 0, st>>>(Ll, kb);
-      }
-    }
-    chol_fixup_kernel<<<CN, 256, 0, st>>>(Ll, Dfac);
-    chol_dinv_kernel<<<CNB, 32, 0, st>>>(Ll);
+    // scal[0] = max diagonal (as ordered bits), scal[1] = barrier counter
+    FPS_CUDA(cudaMemsetAsync(scal, 0, 2 * sizeof(double), st));
+    // cooperative launch: the 66 CTAs wait on one another at the grid barriers, so the driver must place them all at once
+    double lam = h_lambdas[li], nt = (double)n_total, nbt = (double)nbc_total, jit = h_jitter ? h_jitter[li] : 0.0;
+    unsigned long long* dmax = reinterpret_cast<unsigned long long*>(scal);
+    unsigned* bar = reinterpret_cast<unsigned*>(scal + 1);
+    int* info_l = info + li;
+    void* args[] = {(void*)&G, (void*)&Gbc, (void*)&s, &lam, &nt, &nbt, (void*)&d_counts, &jit, &Ll, &Dfac, &dmax, &bar, &info_l};
+    FPS_CUDA(cudaLaunchCooperativeKernel((const void*)chol_fused_kernel, dim3(CF_CTAS), dim3(256), args, 0, st));
   }
-  count_launch(n_lambda * (4 + CNB + (CNB - 1)));
+  count_launch(n_lambda);
   FPS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -589,9 +491,84 @@ int chol_init(fps_ctx* ctx) {
   return 0;
 }
 
-int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
-                          const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st) {
+// ---- few right-hand sides (B <= 8): the solve as GEMVs with the explicit inverse --------------------------------------
+// out[i][c] = beta base[i][c] + alpha sum_k M[i][k] v[k][c] over the lower (k <= i) or upper (k >= i) part of row i of a
+// (CN x CN) matrix; one warp per row, v staged in shared memory.  All 704 rows run in parallel on 88 CTAs; the
+// substitution kernel above needs 44 dependent block steps on ONE SM (0.6 ms for a single right-hand side).
+template <bool UPPER>
+__global__ void __launch_bounds__(256)
+tri_gemv_kernel(const double* __restrict__ M, const double* __restrict__ v, int64_t ldv, double alpha,
+                const double* __restrict__ base, int64_t ldb, double beta, double* __restrict__ out, int64_t ldo, int B) {
+  __shared__ double vs[CN * SC];
+  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
+  for (int e = t; e < CN * SC; e += 256) {
+    const int k = e / SC, c = e % SC;
+    vs[e] = (c < B) ? __ldcg(v + (int64_t)k * ldv + c) : 0.0;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= CN) return;
+  const int k0 = UPPER ? i : 0, k1 = UPPER ? CN : i + 1;
+  double acc[SC];
+#pragma unroll
+  for (int c = 0; c < SC; ++c) acc[c] = 0.0;
+  const double* row = M + (size_t)i * CN;
+  for (int k = (k0 & ~31) + lane; k < k1; k += 32) {
+    if (k < k0) continue;
+    const double m = __ldcg(row + k);
+#pragma unroll
+    for (int c = 0; c < SC; ++c) acc[c] = fma(m, vs[k * SC + c], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < SC; ++c)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  if (lane < B) {
+    double r = 0.0;
+#pragma unroll
+    for (int c = 0; c < SC; ++c) r = (lane == c) ? acc[c] : r;
+    r *= alpha;
+    if (base) r = fma(beta, __ldcg(base + (int64_t)i * ldb + lane), r);
+    out[(int64_t)i * ldo + lane] = r;
+  }
+}
+
+// bias_c = -(s^T W_c - sum_bc_c) / N_bc  (solver.py:306), one warp per column
+__global__ void bias_kernel(const double* __restrict__ W, int64_t ldw, int B, const double* __restrict__ s,
+                            const double* __restrict__ sum_bc, double inv_nbc, double* __restrict__ bias) {
+  const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (c >= B) return;
+  double acc = 0.0;
+  for (int r = lane; r < F; r += 32) acc = fma(s[r], W[(int64_t)r * ldw + c], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) bias[c] = -(acc - sum_bc[c]) * inv_nbc;
+}
+
+int launch_solve_factored(const fps_ctx* ctx, const double* L, const double* R, int64_t ldr, int B, double scale,
+                          const double* s, const double* sum_bc, int64_t nbc_total, double* W, double* bias,
+                          cudaStream_t st) {
   if (B <= 0) return 0;
+  static const int gemv_env = getenv("FPS_SOLVE_GEMV") ? atoi(getenv("FPS_SOLVE_GEMV")) : 1;
+  if (B <= SC && gemv_env) {
+    // y0 = X b, r = b - L y0, y = y0 + X r (one refinement step against L restores the backward stability of
+    // substitution: the explicit inverse alone leaves a residual ~ cond(L) eps);  then the same with the transposes.
+    // b = scale R.  Temporaries (5 x 704 x 8 doubles) live behind the factorisation's scratch in the split-K workspace.
+    const double* X = L + (size_t)(CN + CB) * CN;
+    double* tmp = ctx->partial + 8 + (size_t)CNB * CB * CB;
+    double *y0 = tmp, *r = tmp + CN * SC, *y = tmp + 2 * CN * SC, *w0 = tmp + 3 * CN * SC, *r2 = tmp + 4 * CN * SC;
+    const int grid = CN / 8;
+    tri_gemv_kernel<false><<<grid, 256, 0, st>>>(X, R, ldr, scale, nullptr, 0, 0.0, y0, SC, B);
+    tri_gemv_kernel<false><<<grid, 256, 0, st>>>(L, y0, SC, -1.0, R, ldr, scale, r, SC, B);
+    tri_gemv_kernel<false><<<grid, 256, 0, st>>>(X, r, SC, 1.0, y0, SC, 1.0, y, SC, B);
+    tri_gemv_kernel<true><<<grid, 256, 0, st>>>(X, y, SC, 1.0, nullptr, 0, 0.0, w0, SC, B);
+    tri_gemv_kernel<true><<<grid, 256, 0, st>>>(L, w0, SC, -1.0, y, SC, 1.0, r2, SC, B);
+    tri_gemv_kernel<true><<<grid, 256, 0, st>>>(X, r2, SC, 1.0, w0, SC, 1.0, W, ldr, B);
+    bias_kernel<<<1, 256, 0, st>>>(W, ldr, B, s, sum_bc, 1.0 / (double)nbc_total, bias);
+    count_launch(7);
+    FPS_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = SOLVE_SMEM;
   solve_factored_kernel<<<(B + SC - 1) / SC, 256, smem, st>>>(L, R, ldr, B, scale, s, sum_bc, 1.0 / (double)nbc_total,
                                                               W, bias);

@@ -202,7 +202,7 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   FPS_CUDA(cudaMalloc(&ctx->tc_sched, 2 * sizeof(int)));
   FPS_CUDA(cudaMemset(ctx->tc_sched, 0, 2 * sizeof(int)));
   ctx->workspace_bytes = 4 * plane + ctx->partial_bytes;
-  if (tc_init(ctx) || chol_init(ctx) || sources_init(ctx)) { fps_destroy(ctx); return 3; }
+  if (tc_init(ctx) || chol_init(ctx) || sources_init(ctx) || stream_init(ctx)) { fps_destroy(ctx); return 3; }
   *out = ctx;
   return 0;
 }
@@ -212,6 +212,7 @@ int fps_destroy(fps_ctx* ctx) {
   int prev_device = -1;
   cudaGetDevice(&prev_device);   // the caller's current device is restored below (torch relies on it)
   cudaSetDevice(ctx->device);
+  comm_destroy(ctx);
   tc_destroy(ctx);
   gram_i8_destroy(ctx);
   recon_i8_destroy(ctx);
@@ -531,7 +532,7 @@ int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64
   FPS_REQUIRE(ctx && L64 && R64 && s64 && sum_bc64 && W64 && bias64, "fps_solve_factored: null argument");
   FPS_REQUIRE(ldr >= B && nbc_total > 0, "fps_solve_factored: bad argument");
   ProfScope ps(ctx, FPS_PROF_TRISOLVE, (cudaStream_t)stream);
-  return launch_solve_factored(L64, R64, ldr, B, scale, s64, sum_bc64, nbc_total, W64, bias64, (cudaStream_t)stream);
+  return launch_solve_factored(ctx, L64, R64, ldr, B, scale, s64, sum_bc64, nbc_total, W64, bias64, (cudaStream_t)stream);
 }
 
 int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,

@@ -100,6 +100,8 @@ struct fps_ctx {
   fps::Xop* xop_tmp;      // context-owned descriptors for the uncached entry points: [0] A operand, [1] scratch
   unsigned* dh_cal_cmax;  // FPW words: max |DH| per feature over the calibration sample (float bits); 0 = not calibrated
   int dh_cal_valid;
+  void* comm;             // NCCL communicator of this context (comm.cu), null until fps_comm_init
+  int comm_rank, comm_world;
   int gain_checked;       // the accumulator-gain compensation of layer_tc.cu has been checked against the fp32 engine
   int gain_off;           // 1: compensation disabled for this weight set (the check found it harmful)
   double cal_err[4];      // rel-L2 vs the fp32 engine on the calibration sample: {H, DH} with gain, {H, DH} without
@@ -152,6 +154,13 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
 int tc_init(fps_ctx* ctx);
 int chol_init(fps_ctx* ctx);
 int sources_init(fps_ctx* ctx);
+int stream_init(fps_ctx* ctx);
+void comm_destroy(fps_ctx* ctx);
+// streaming single / few right-hand-side kernels (stream_f32.cu); return 1 = not applicable (fall back), 0 = done
+int launch_project_stream(const fps_ctx* ctx, const float* A, int64_t lda, const float* Fm, int64_t ldf, int B, int64_t n,
+                          double* partial, int* nctas_out, cudaStream_t st);
+int launch_recon_stream(const fps_ctx* ctx, const float* A, int64_t n, int64_t lda, const double* W, int64_t ldw,
+                        const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
 void tc_destroy(fps_ctx* ctx);
 
 // C (M x Ncols, ldc) fp64 += A^T B over n rows; A (n, lda) fp32 M columns, B (n, ldb) fp32 Ncols columns.
@@ -190,8 +199,9 @@ int launch_colsum(const float* A, int64_t n, int64_t ld, double* s64, cudaStream
 int launch_assemble_factor(const fps_ctx* ctx, const double* G, const double* Gbc, const double* s, int64_t n_total,
                            int64_t nbc_total, const double* d_counts, const double* h_lambdas, const double* h_jitter,
                            int n_lambda, double* L, int* info, cudaStream_t st);
-int launch_solve_factored(const double* L, const double* R, int64_t ldr, int B, double scale, const double* s,
-                          const double* sum_bc, int64_t nbc_total, double* W, double* bias, cudaStream_t st);
+int launch_solve_factored(const fps_ctx* ctx, const double* L, const double* R, int64_t ldr, int B, double scale,
+                          const double* s, const double* sum_bc, int64_t nbc_total, double* W, double* bias,
+                          cudaStream_t st);
 int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
                        const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
 int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st);

@@ -15,6 +15,7 @@
 // second kernel, so results are bit-reproducible for a given (n, chunking) - no fp64 atomics.
 #include "fps_common.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace fps {
 
@@ -349,6 +350,23 @@ int launch_atb_t(const fps_ctx* ctx, const TA* A, int64_t lda, int M, const TB* 
                  double* C, int64_t ldc, bool symmetric, cudaStream_t st) {
   if (n <= 0 || M <= 0 || Nc <= 0) return 0;
   FPS_REQUIRE(M <= FP, "atb: M=%d exceeds %d", M, FP);
+  if (!symmetric && Nc <= 8 && M == FP && std::is_same<TA, float>::value && std::is_same<TB, float>::value) {
+    // TMA-staged streaming form (stream_f32.cu); the register-staged kernel below serves what it does not take
+    int nctas = 0;
+    const int rc = launch_project_stream(ctx, reinterpret_cast<const float*>(A), lda, reinterpret_cast<const float*>(B), ldb,
+                                         Nc, n, ctx->partial, &nctas, st);
+    if (rc > 1) return rc;
+    if (rc == 0) {
+      const int nbk = Nc == 1 ? 1 : Nc == 2 ? 2 : Nc <= 4 ? 4 : 8;
+      if (nbk == 1) atb_small_reduce_kernel<1><<<(M * 1 + 255) / 256, 256, 0, st>>>(ctx->partial, nctas, M, Nc, C, ldc);
+      else if (nbk == 2) atb_small_reduce_kernel<2><<<(M * 2 + 255) / 256, 256, 0, st>>>(ctx->partial, nctas, M, Nc, C, ldc);
+      else if (nbk == 4) atb_small_reduce_kernel<4><<<(M * 4 + 255) / 256, 256, 0, st>>>(ctx->partial, nctas, M, Nc, C, ldc);
+      else atb_small_reduce_kernel<8><<<(M * 8 + 255) / 256, 256, 0, st>>>(ctx->partial, nctas, M, Nc, C, ldc);
+      count_launch();
+      FPS_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   if (!symmetric && Nc <= 8) {
     int64_t ctas = std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 63) / 64);
     ctas = std::min<int64_t>(ctas, (int64_t)(ctx->partial_bytes / (768 * 8 * sizeof(double))));
@@ -597,6 +615,11 @@ int launch_reconstruct_t(const fps_ctx* ctx, const TA* A, int64_t n, int64_t ld,
   if (n <= 0 || B <= 0) return 0;
   FPS_REQUIRE(ld % 4 == 0 && (uintptr_t)A % 16 == 0 && ld >= FP,
               "reconstruct: A must be 16-byte aligned, ld %% 4 == 0, ld >= %d", FP);
+  if (std::is_same<TA, float>::value && std::is_same<TO, float>::value) {
+    const int rc = launch_recon_stream(ctx, reinterpret_cast<const float*>(A), n, ld, W, ldw, bias, B,
+                                       reinterpret_cast<float*>(out), ldo, st);
+    if (rc != 1) return rc;
+  }
   if (B <= 4) {
     const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
     if (B == 1) nn_small_kernel<1, TA, TO><<<(unsigned)blocks, 256, 0, st>>>(A, n, ld, W, ldw, bias, B, out, ldo);

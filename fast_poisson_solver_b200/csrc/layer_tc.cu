@@ -435,12 +435,14 @@ __device__ __forceinline__ void layer_tc_body(const CUtensorMap& tmWhi, const CU
         if (planes) {
           const int64_t pg = P.point0 + (r0 >> 2);           // first of this thread's 32 points (a multiple of 32)
           int8_t* base = P.gplanes + (((pg >> 7) * 4) * FPW + f) * 128 + (pg & 127);
+          // one 32-byte store per digit (STG.256): whole sectors - two 16-byte stores per run cost twice the sector
+          // transactions and put the last layer 1.5 ms behind the hidden ones
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            uint4* dst = reinterpret_cast<uint4*>(base + (int64_t)s4 * FPW * 128);
-            dst[0] = make_uint4(dg[s4][0], dg[s4][1], dg[s4][2], dg[s4][3]);
-            dst[1] = make_uint4(dg[s4][4], dg[s4][5], dg[s4][6], dg[s4][7]);
-          }
+          for (int s4 = 0; s4 < 4; ++s4)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(base + (int64_t)s4 * FPW * 128),
+                         "r"(dg[s4][0]), "r"(dg[s4][1]), "r"(dg[s4][2]), "r"(dg[s4][3]), "r"(dg[s4][4]), "r"(dg[s4][5]),
+                         "r"(dg[s4][6]), "r"(dg[s4][7])
+                         : "memory");
         }
       } else if (f_ok) {
         if (S == 4) {

@@ -43,7 +43,7 @@ import numpy as np
 import torch
 
 from . import _lib, weights as _weights
-from .parallel import PackedNormal, allreduce_sum
+from .parallel import Communicator, PackedNormal
 
 F, FP = _lib.F, _lib.FP
 _JITTER_LADDER = [0.0, 8.0, 128.0, 2048.0, 32768.0, 2.0 ** 20, 2.0 ** 26, 2.0 ** 32]  # x eps x max_diag
@@ -160,6 +160,7 @@ class Solver:
         self._cache_planes = cache_planes if cache_planes is not None else (None if env is None else env != "0")
         self._exact_min = int(self._lib.fps_exact_min_rows())
         self._reserved = (0, 0)
+        self._comm = None
 
     def _fn(self, name):
         return getattr(self._lib, name + ("_f64" if self._fdtype == torch.float64 else ""))
@@ -216,7 +217,10 @@ class Solver:
                        "fps_reserve_workspace")
 
     def _allreduce(self, t):
-        allreduce_sum(t, self.process_group)
+        """The path's exchange step: an in-place fp64 sum over the ranks (csrc/comm.cu through parallel.Communicator)."""
+        if self._comm is None:
+            self._comm = Communicator(self, self.process_group)
+        self._comm.allreduce(t)
 
     def _enqueue_factor(self, jitter):
         nl = self.n_lambdas
@@ -381,7 +385,7 @@ class Solver:
                        "fps_colsum_accum")                                  # solver.py:176-178
         packed.set_counts(n_loc, nbc_loc)
         if self.distributed:
-            packed.allreduce(self.process_group)  # the path's one exchange step
+            self._allreduce(packed.buf)            # the path's one exchange step
             self._counts_dev = packed.buf[-2:]
             self.NO = self.NdO = None              # read back with the final synchronise (see _publish)
         else:
@@ -475,7 +479,7 @@ class Solver:
         sc = (C.c_float * 24)(*p["act_scales"])
         _lib.check(self._lib.fps_set_calibration(self._ctx, sc, int(p.get("gain_on", -1))), "fps_set_calibration")
         self._refactor_pending = False
-        if list(p["lambdas"]) == list(self.lambdas_pde):
+        if list(p["lambdas"]) == list(self.lambdas_pde) and tuple(p["L64"].shape[1:]) == (_lib.LROWS, FP):
             self._L64, self.jitter = p["L64"].to(self._tdev), p["jitter"]
         else:
             self._factor()

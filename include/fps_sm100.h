@@ -38,7 +38,7 @@ extern "C" {
 #define FPS_FP 704       /* FPS_F padded to a multiple of 64                                  */
 #define FPS_K0 400       /* 2 * ffm.num Fourier inputs, resources/infos.yaml:843-848          */
 #define FPS_NFREQ 200
-#define FPS_LROWS 736    /* rows of one Cholesky factor buffer: 704 of L + 32 of diagonal-block inverses */
+#define FPS_LROWS 1440   /* rows of one factor buffer: 704 of L + 32 of diagonal-block inverses + 704 of L^-1 */
 #define FPS_NHIDDEN 5    /* depth-1 Linear(700,700)+Tanh blocks, model.py:49-60               */
 
 #define FPS_ENGINE_SIMT 0     /* fp32 FFMA layer kernel (bring-up / cross-check engine)        */
@@ -112,8 +112,10 @@ int fps_colsum_accum(fps_ctx* ctx, const float* A, int64_t n, int64_t ld, double
  * (solver.py:305):  for every lambda
  *     LHS = lambda/N * G + ( Gbc - s s^T / N_bc ) / N_bc          (centering matrix folded in)
  * then the lower Cholesky factor L of LHS is left in L64[(i), :FPS_FP, :] of the (n_lambda, FPS_LROWS,
- * FPS_FP) float64 buffer (mirrored into the upper triangle); rows FPS_FP.. hold the inverses of the 22
- * diagonal 32x32 blocks that fps_solve_factored applies.  h_lambdas / h_jitter are HOST arrays of
+ * FPS_FP) float64 buffer (mirrored into the upper triangle); rows FPS_FP .. FPS_FP + 31 hold the inverses of the 22
+ * diagonal 32x32 blocks that the many-right-hand-side solve applies, rows FPS_FP + 32 .. the explicit inverse L^-1 (lower
+ * triangle; its transpose above the diagonal) that the solve for <= 8 right-hand sides applies as GEMVs with one step
+ * of refinement against L.  h_lambdas / h_jitter are HOST arrays of
  * n_lambda entries; h_jitter (may be NULL = 0) is an absolute diagonal shift added to LHS - the
  * matrix has cond ~1e15 and is exactly singular when N + N_bc < 700, so the caller starts at 0 and
  * raises the shift only when info reports a breakdown.  info (device int[n_lambda]) receives 0 or
@@ -246,6 +248,20 @@ int fps_fd_solve(fps_ctx* ctx, int Gx, int Gy, double hx, double hy, const doubl
                  int B, double* U, int64_t ldu, void* work, size_t work_bytes, void* stream);
 int fps_fd_solve_f32(fps_ctx* ctx, int Gx, int Gy, double hx, double hy, const float* F, int64_t ldf, const double* bc,
                      int B, double* U, int64_t ldu, void* work, size_t work_bytes, void* stream);
+
+/* ---- multi-GPU: the path's one exchange step -------------------------------------------------------
+ * Collocation points shard across GPUs (one process and one context per GPU); every sum over points is an all-reduce:
+ * the packed buffer [G | Gbc | s | N | N_bc] (FPS_PACK_DOUBLES float64) once per precompute, the projected right-hand
+ * sides (FPS_FP x B float64, plus the boundary sums) once per solve.  The reference has no collective (it runs on one
+ * device, solver.py:162-199).  The communicator is NCCL, resolved with dlopen at the first call:
+ *   rank 0:       fps_comm_unique_id(id)        -> 128 bytes, handed to the other ranks by ANY means (file, MPI, ...)
+ *   every rank:   fps_comm_init(ctx, id, rank, world)
+ *   then:         fps_allreduce_f64(ctx, buf, count, stream)      in place, SUM, enqueued on `stream`                */
+#define FPS_COMM_ID_BYTES 128
+int fps_comm_unique_id(void* h_id128);
+int fps_comm_init(fps_ctx* ctx, const void* h_id128, int rank, int world);
+int fps_allreduce_f64(fps_ctx* ctx, double* buf, int64_t count, void* stream);
+int fps_comm_destroy(fps_ctx* ctx);
 
 /* ---- instrumentation (bench.py / profiles) ----------------------------------------------------
  * fps_launch_count: number of kernels this library has launched in this process (all contexts).

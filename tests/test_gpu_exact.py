@@ -294,7 +294,7 @@ def test_fused_cholesky_equals_stepwise_and_numpy(make_solver):
     pack[-2:] = (n, nbc)
     dp = torch.tensor(pack, device="cuda")
     lam = [0.25, 3.0]
-    L = torch.empty((2, 736, 704), dtype=torch.float64, device="cuda")
+    L = torch.empty((2, _lib.LROWS, 704), dtype=torch.float64, device="cuda")
     info = torch.ones(2, dtype=torch.int32, device="cuda")
     _lib.check(lib.fps_assemble_factor_packed(ctx, dp.data_ptr(), (C.c_double * 2)(*lam), None, 2, L.data_ptr(),
                                               info.data_ptr(), st), "factor_packed")
@@ -304,7 +304,10 @@ def test_fused_cholesky_equals_stepwise_and_numpy(make_solver):
         Ld = L[i, :704].cpu().numpy()
         assert np.allclose(np.tril(Ld[:700, :700]), np.linalg.cholesky(LHS), rtol=1e-10, atol=1e-12)
         assert np.allclose(Ld, Ld.T) and np.allclose(Ld[700:, 700:], np.eye(4))
-        Di = L[i, 704:].cpu().numpy()                      # inverses of the 22 diagonal blocks
+        Xf = L[i, 736:].cpu().numpy()                      # explicit inverse: lower triangle X = L^-1, upper X^T
+        assert np.allclose(np.tril(Xf) @ np.tril(Ld), np.eye(704), atol=1e-9)
+        assert np.allclose(Xf, Xf.T)
+        Di = L[i, 704:736].cpu().numpy()                      # inverses of the 22 diagonal blocks
         for kb in (0, 7, 21):
             blk = np.tril(Ld[32 * kb: 32 * kb + 32, 32 * kb: 32 * kb + 32])
             assert np.allclose(Di[:, 32 * kb: 32 * kb + 32] @ blk, np.eye(32), atol=1e-9)

@@ -234,7 +234,7 @@ def test_cholesky_and_batched_solve_kernels(solver_factory):
     sv = np.zeros(704); sv[:700] = Hb.sum(0)
     lam = [0.5, 2.0]
     dG, dGb, dsv = (torch.tensor(v, device="cuda") for v in (G, Gb, sv))
-    L = torch.empty((2, 736, 704), dtype=torch.float64, device="cuda")
+    L = torch.empty((2, _lib.LROWS, 704), dtype=torch.float64, device="cuda")
     info = torch.ones(2, dtype=torch.int32, device="cuda")
     _lib.check(lib.fps_assemble_factor(ctx, dG.data_ptr(), dGb.data_ptr(), dsv.data_ptr(), n, nbc,
                                        (C.c_double * 2)(*lam), None, 2, L.data_ptr(), info.data_ptr(), st), "factor")

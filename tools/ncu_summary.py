@@ -37,7 +37,39 @@ def full_summary(rep, dst, header):
             w.writerow([r[i] for i in idx])
     return [[r[i] for i in idx] for r in rows]
 
+def round_summary(tag, cmd):
+    """profiles/<tag>_launch_shares.csv, profiles/<tag>_<kernel>_ncu_full_summary.csv for every gpurun_out/<tag>_prof_*.ncu-rep
+    and profiles/<tag>_ncu_traffic.json (dram bytes per launch per kernel, read by bench.py's roofline.traffic)."""
+    import glob, json, os
+
+    launch_shares(f"gpurun_out/{tag}_launches.csv", f"profiles/{tag}_launch_shares.csv",
+                  [f"# {tag} ncu launch list of: {cmd}",
+                   "# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)"])
+    traffic = {}
+    for rep in sorted(glob.glob(f"gpurun_out/{tag}_prof_*.ncu-rep")):
+        name = os.path.basename(rep)[len(tag) + 6:-8]
+        rows = full_summary(rep, f"profiles/{tag}_{name}_ncu_full_summary.csv",
+                            [f"# {tag} ncu --set full --clock-control none --import-source on ({name}) of: {cmd}"])
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            u = dict(zip(hdr, units))
+
+            def to_bytes(k):
+                v = float(d[k].replace(",", ""))
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[k]]
+
+            traffic.setdefault(d["Kernel Name"], []).append(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
+            print(name, d["Kernel Name"][:60], d["gpu__time_duration.sum"], u["gpu__time_duration.sum"],
+                  "tensor %", d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                  "dram %", d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"))
+    json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(f"profiles/{tag}_ncu_traffic.json", "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) == 3:
+        round_summary(sys.argv[1], sys.argv[2])
+        sys.exit(0)
     tag = sys.argv[1]
     cmd = sys.argv[2]
     for l in launch_shares(f"gpurun_out/launches_{tag}.csv", f"profiles/{tag}_launch_shares.csv",
