@@ -247,14 +247,15 @@ def read_profile(solver):
     return out
 
 
-def ncu_traffic(kernel_substr):
+def ncu_traffic(capture, points_per_launch=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
-    capture of this round (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    capture of this round (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py), scaled to the points one launch
+    of THIS run covers; None when no capture is committed."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
-        for k, v in t.items():
-            if kernel_substr in k:
-                return v
+        for k, v in t["bytes_per_launch"].items():
+            if k.startswith(capture + ":"):
+                return v * (points_per_launch / t["points_per_layer_launch"] if points_per_launch else 1.0)
     except Exception:
         pass
     return None
@@ -519,7 +520,7 @@ def run_ours(args):
                                     "kernel also sits at the L2->SM operand-feed cap (DESIGN.md section 4)",
                      "launches": int(hid_n), "avg_launch_ms": hid_ms / hid_n if hid_n else None,
                      "points_per_launch": 4 * args.steps * n_pts / hid_n if hid_n else None,
-                     "traffic": ncu_traffic("layer_tc_pair_kernel<4, false"),
+                     "traffic": ncu_traffic("hidden", 4 * args.steps * n_pts / hid_n if hid_n else None),
                      "traffic_unit": "bytes/launch: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
                                      "(profiles/r02_ncu_traffic.json); null = no capture committed for this build"},
         "int8_peak": i8,

@@ -84,9 +84,10 @@ SIGNATURES = {
     "fps_fd_solve": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, C.c_size_t, _vp]),
     "fps_fd_solve_f32": (_i32, [_vp, _i32, _i32, _f64, _f64, _vp, _i64, _vp, _i32, _vp, _i64, _vp, C.c_size_t, _vp]),
     "fps_comm_unique_id": (_i32, [_vp]),
-    "fps_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "fps_comm_init": (_i32, [C.POINTER(_vp), _i32, _vp, _i32, _i32]),
     "fps_allreduce_f64": (_i32, [_vp, _vp, _i64, _vp]),
     "fps_comm_destroy": (_i32, [_vp]),
+    "fps_comm_abort": (_i32, [_vp]),
     "fps_launch_count": (_i64, []),
     "fps_profile_enable": (_i32, [_vp, _i32]),
     "fps_profile_reset": (_i32, [_vp]),

@@ -1,4 +1,4 @@
-// The path's one exchange step behind the C ABI: an NCCL communicator per context and an in-place
+// The path's one exchange step behind the C ABI: an NCCL communicator per process / GPU and an in-place
 // fp64 sum all-reduce for (a) the packed normal-equation buffer [G | Gbc | s | N | N_bc] of precompute and (b) the
 // projected right-hand sides of solve.  The reference has no collective at all (solver.py:162-199 runs on one device);
 // a maintainer binding the C ABI (INTEGRATION.md route B) needs nothing but a way to hand rank 0's 128-byte
@@ -26,6 +26,7 @@ struct NcclApi {
   CommInitRankFn comm_init_rank = nullptr;
   AllReduceFn all_reduce = nullptr;
   CommDestroyFn comm_destroy = nullptr;
+  CommDestroyFn comm_abort = nullptr;
   GetErrorStringFn get_error_string = nullptr;
 };
 
@@ -41,6 +42,7 @@ static int nccl_load() {
   g_nccl.comm_init_rank = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
   g_nccl.all_reduce = (AllReduceFn)dlsym(h, "ncclAllReduce");
   g_nccl.comm_destroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
+  g_nccl.comm_abort = (CommDestroyFn)dlsym(h, "ncclCommAbort");
   g_nccl.get_error_string = (GetErrorStringFn)dlsym(h, "ncclGetErrorString");
   FPS_REQUIRE(g_nccl.get_unique_id && g_nccl.comm_init_rank && g_nccl.all_reduce && g_nccl.comm_destroy,
               "fps_comm: libnccl.so.2 lacks the expected symbols");
@@ -58,12 +60,14 @@ static int nccl_load() {
     }                                                                                                         \
   } while (0)
 
-void comm_destroy(fps_ctx* ctx) {
-  if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(static_cast<NcclComm_t>(ctx->comm));
-  ctx->comm = nullptr;
-}
-
 }  // namespace fps
+
+// A communicator is its own object (not part of a context): one per process / GPU serves every Solver of that process, and
+// its lifetime is explicit - ncclCommDestroy is an intra-node collective, so it must never run from a garbage collector.
+struct fps_comm {
+  fps::NcclComm_t nccl;
+  int device, rank, world;
+};
 
 using namespace fps;
 
@@ -79,13 +83,13 @@ int fps_comm_unique_id(void* h_id) {
   return 0;
 }
 
-int fps_comm_init(fps_ctx* ctx, const void* h_id, int rank, int world) {
-  FPS_REQUIRE(ctx && h_id && world >= 1 && rank >= 0 && rank < world, "fps_comm_init: bad argument");
+int fps_comm_init(fps_comm** out, int device, const void* h_id, int rank, int world) {
+  FPS_REQUIRE(out && h_id && world >= 1 && rank >= 0 && rank < world, "fps_comm_init: bad argument");
+  *out = nullptr;
   if (int rc = nccl_load()) return rc;
-  comm_destroy(ctx);
   int prev = -1;
   cudaGetDevice(&prev);
-  FPS_CUDA(cudaSetDevice(ctx->device));
+  FPS_CUDA(cudaSetDevice(device));
   NcclId id;
   memcpy(&id, h_id, sizeof(id));
   NcclComm_t comm = nullptr;
@@ -93,25 +97,37 @@ int fps_comm_init(fps_ctx* ctx, const void* h_id, int rank, int world) {
   if (prev >= 0) cudaSetDevice(prev);
   FPS_REQUIRE(r == 0, "fps_comm_init: ncclCommInitRank failed (%d: %s)", r,
               g_nccl.get_error_string ? g_nccl.get_error_string(r) : "?");
-  ctx->comm = comm;
-  ctx->comm_rank = rank;
-  ctx->comm_world = world;
+  fps_comm* c = new fps_comm();
+  c->nccl = comm;
+  c->device = device;
+  c->rank = rank;
+  c->world = world;
+  *out = c;
   return 0;
 }
 
-int fps_allreduce_f64(fps_ctx* ctx, double* buf, int64_t count, void* stream) {
-  FPS_REQUIRE(ctx && buf && count >= 0, "fps_allreduce_f64: bad argument");
-  FPS_REQUIRE(ctx->comm, "fps_allreduce_f64: call fps_comm_init first");
+int fps_allreduce_f64(fps_comm* comm, double* buf, int64_t count, void* stream) {
+  FPS_REQUIRE(comm && comm->nccl && buf && count >= 0, "fps_allreduce_f64: bad argument");
   if (count == 0) return 0;
   // in place, SUM (ncclSum = 0) of doubles (ncclDouble = 8): reproducible for a fixed rank count (NCCL's ring / tree
   // order is deterministic for a given topology and size)
-  FPS_NCCL(g_nccl.all_reduce(buf, buf, (size_t)count, 8, 0, static_cast<NcclComm_t>(ctx->comm), (cudaStream_t)stream));
+  FPS_NCCL(g_nccl.all_reduce(buf, buf, (size_t)count, 8, 0, comm->nccl, (cudaStream_t)stream));
   return 0;
 }
 
-int fps_comm_destroy(fps_ctx* ctx) {
-  FPS_REQUIRE(ctx, "fps_comm_destroy: null ctx");
-  comm_destroy(ctx);
+// COLLECTIVE: every rank of the node must call it (ncclCommDestroy finalises the communicator together with its peers).
+int fps_comm_destroy(fps_comm* comm) {
+  if (!comm) return 0;
+  if (comm->nccl && g_nccl.comm_destroy) g_nccl.comm_destroy(comm->nccl);
+  delete comm;
+  return 0;
+}
+
+// Local teardown without coordination (error paths, interpreter shutdown).
+int fps_comm_abort(fps_comm* comm) {
+  if (!comm) return 0;
+  if (comm->nccl && g_nccl.comm_abort) g_nccl.comm_abort(comm->nccl);
+  delete comm;
   return 0;
 }
 

@@ -212,7 +212,6 @@ int fps_destroy(fps_ctx* ctx) {
   int prev_device = -1;
   cudaGetDevice(&prev_device);   // the caller's current device is restored below (torch relies on it)
   cudaSetDevice(ctx->device);
-  comm_destroy(ctx);
   tc_destroy(ctx);
   gram_i8_destroy(ctx);
   recon_i8_destroy(ctx);

@@ -100,8 +100,6 @@ struct fps_ctx {
   fps::Xop* xop_tmp;      // context-owned descriptors for the uncached entry points: [0] A operand, [1] scratch
   unsigned* dh_cal_cmax;  // FPW words: max |DH| per feature over the calibration sample (float bits); 0 = not calibrated
   int dh_cal_valid;
-  void* comm;             // NCCL communicator of this context (comm.cu), null until fps_comm_init
-  int comm_rank, comm_world;
   int gain_checked;       // the accumulator-gain compensation of layer_tc.cu has been checked against the fp32 engine
   int gain_off;           // 1: compensation disabled for this weight set (the check found it harmful)
   double cal_err[4];      // rel-L2 vs the fp32 engine on the calibration sample: {H, DH} with gain, {H, DH} without
@@ -155,7 +153,6 @@ int tc_init(fps_ctx* ctx);
 int chol_init(fps_ctx* ctx);
 int sources_init(fps_ctx* ctx);
 int stream_init(fps_ctx* ctx);
-void comm_destroy(fps_ctx* ctx);
 // streaming single / few right-hand-side kernels (stream_f32.cu); return 1 = not applicable (fall back), 0 = done
 int launch_project_stream(const fps_ctx* ctx, const float* A, int64_t lda, const float* Fm, int64_t ldf, int B, int64_t n,
                           double* partial, int* nctas_out, cudaStream_t st);

@@ -68,47 +68,60 @@ def allreduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class Communicator:
-    """The sum all-reduce of the path for one Solver.
+    """The sum all-reduce of the path.
 
     On CUDA it is the library's own NCCL communicator behind the C ABI (csrc/comm.cu: fps_comm_init /
-    fps_allreduce_f64, enqueued on the solver's stream): rank 0 creates the 128-byte ncclUniqueId and torch.distributed
-    merely carries it to the other ranks - the one thing a non-torch host would do by file or MPI.  FPS_COMM=torch (or a
+    fps_allreduce_f64, enqueued on the caller's stream): rank 0 creates the 128-byte ncclUniqueId and torch.distributed
+    merely carries it to the other ranks - the one thing a non-torch host would do by file or MPI.  ONE communicator per
+    (device, process group) serves every Solver of the process and lives until the process ends: ncclCommDestroy is a
+    collective, so it must not depend on when a garbage collector happens to run on each rank.  FPS_COMM=torch (or a
     failing NCCL initialisation) keeps everything on torch.distributed; CPU tensors (the gloo tests) always go there."""
 
-    def __init__(self, solver, group=None):
+    _cache = {}
+
+    def __init__(self, lib, dev_index, group=None):
         import os
 
         import torch.distributed as dist
 
-        self.group, self.solver, self.native = group, solver, False
+        self.group, self.lib, self.handle = group, lib, None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if os.environ.get("FPS_COMM", "abi") != "abi":
             return
+        key = (dev_index, id(group) if group is not None else None)
+        if key in Communicator._cache:
+            self.handle = Communicator._cache[key]
+            return
         import ctypes as C
 
-        from . import _lib
-
+        dev = torch.device("cuda", dev_index)
         ident = [None]
         if self.rank == 0:
             buf = (C.c_char * 128)()
-            if solver._lib.fps_comm_unique_id(buf) == 0:
+            if lib.fps_comm_unique_id(buf) == 0:
                 ident[0] = bytes(buf)
-        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        ok = 0
+        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group,
+                                   device=dev)
+        handle, ok = C.c_void_p(), 0
         if ident[0] is not None:
-            with torch.cuda.device(solver._dev_index):
-                ok = 1 if solver._lib.fps_comm_init(solver._ctx, ident[0], self.rank, self.world) == 0 else 0
-        flag = torch.tensor([float(ok)], device=solver._tdev)
+            ok = 1 if lib.fps_comm_init(C.byref(handle), dev_index, ident[0], self.rank, self.world) == 0 else 0
+        flag = torch.tensor([float(ok)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # every rank must take the same path
-        self.native = flag.item() > 0.5
-        if not self.native and ok:
-            solver._lib.fps_comm_destroy(solver._ctx)
+        if flag.item() > 0.5:
+            self.handle = handle
+        elif ok:
+            lib.fps_comm_abort(handle)
+        Communicator._cache[key] = self.handle
 
-    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
-        if self.native and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous():
+    @property
+    def native(self):
+        return self.handle is not None
+
+    def allreduce(self, t: torch.Tensor, stream=None) -> torch.Tensor:
+        if self.handle is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous():
             from . import _lib
 
-            _lib.check(self.solver._lib.fps_allreduce_f64(self.solver._ctx, t.data_ptr(), t.numel(), self.solver._stream()),
-                       "fps_allreduce_f64")
+            st = stream if stream is not None else torch.cuda.current_stream(t.device).cuda_stream
+            _lib.check(self.lib.fps_allreduce_f64(self.handle, t.data_ptr(), t.numel(), st), "fps_allreduce_f64")
             return t
         return allreduce_sum(t, self.group)

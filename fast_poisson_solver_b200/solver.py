@@ -219,8 +219,8 @@ class Solver:
     def _allreduce(self, t):
         """The path's exchange step: an in-place fp64 sum over the ranks (csrc/comm.cu through parallel.Communicator)."""
         if self._comm is None:
-            self._comm = Communicator(self, self.process_group)
-        self._comm.allreduce(t)
+            self._comm = Communicator(self._lib, self._dev_index, self.process_group)
+        self._comm.allreduce(t, self._stream())
 
     def _enqueue_factor(self, jitter):
         nl = self.n_lambdas

@@ -253,15 +253,19 @@ int fps_fd_solve_f32(fps_ctx* ctx, int Gx, int Gy, double hx, double hy, const f
  * Collocation points shard across GPUs (one process and one context per GPU); every sum over points is an all-reduce:
  * the packed buffer [G | Gbc | s | N | N_bc] (FPS_PACK_DOUBLES float64) once per precompute, the projected right-hand
  * sides (FPS_FP x B float64, plus the boundary sums) once per solve.  The reference has no collective (it runs on one
- * device, solver.py:162-199).  The communicator is NCCL, resolved with dlopen at the first call:
+ * device, solver.py:162-199).  The communicator is NCCL, resolved with dlopen at the first call; it is an object of its
+ * own (one per process / GPU serves any number of contexts):
  *   rank 0:       fps_comm_unique_id(id)        -> 128 bytes, handed to the other ranks by ANY means (file, MPI, ...)
- *   every rank:   fps_comm_init(ctx, id, rank, world)
- *   then:         fps_allreduce_f64(ctx, buf, count, stream)      in place, SUM, enqueued on `stream`                */
+ *   every rank:   fps_comm_init(&comm, device, id, rank, world)            (collective: ncclCommInitRank)
+ *   then:         fps_allreduce_f64(comm, buf, count, stream)              in place, SUM, enqueued on `stream`
+ *   at the end:   fps_comm_destroy(comm)   COLLECTIVE (every rank of the node), or fps_comm_abort(comm) (local)      */
 #define FPS_COMM_ID_BYTES 128
+typedef struct fps_comm fps_comm;
 int fps_comm_unique_id(void* h_id128);
-int fps_comm_init(fps_ctx* ctx, const void* h_id128, int rank, int world);
-int fps_allreduce_f64(fps_ctx* ctx, double* buf, int64_t count, void* stream);
-int fps_comm_destroy(fps_ctx* ctx);
+int fps_comm_init(fps_comm** out, int device, const void* h_id128, int rank, int world);
+int fps_allreduce_f64(fps_comm* comm, double* buf, int64_t count, void* stream);
+int fps_comm_destroy(fps_comm* comm);
+int fps_comm_abort(fps_comm* comm);
 
 /* ---- instrumentation (bench.py / profiles) ----------------------------------------------------
  * fps_launch_count: number of kernels this library has launched in this process (all contexts).

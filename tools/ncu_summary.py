@@ -59,11 +59,15 @@ def round_summary(tag, cmd):
                 v = float(d[k].replace(",", ""))
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[k]]
 
-            traffic.setdefault(d["Kernel Name"], []).append(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
+            traffic.setdefault(name + ":" + d["Kernel Name"].split("(")[0], []).append(
+                to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
             print(name, d["Kernel Name"][:60], d["gpu__time_duration.sum"], u["gpu__time_duration.sum"],
                   "tensor %", d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                   "dram %", d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"))
-    json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(f"profiles/{tag}_ncu_traffic.json", "w"), indent=1)
+    json.dump({"how": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full; key = capture:kernel; layer "
+                      "launches cover one wave of 37 888 points", "points_per_layer_launch": 37888,
+               "bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}},
+              open(f"profiles/{tag}_ncu_traffic.json", "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,14 @@
+set -x
+nvidia-smi -L | wc -l
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/r02_pytest_multi8.log 2>&1; echo "pytest multi rc=$?"
+tail -n 3 gpurun_out/r02_pytest_multi8.log
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err; echo "bench8 rc=$?"
+tail -n 5 gpurun_out/r02_bench_8gpu.err
+python -c "
+import json
+d=[json.loads(l) for l in open('gpurun_out/r02_bench_8gpu.json') if l.startswith('{')][0]
+print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['multi_gpu_parity'])
+s=d['strong']
+for k,v in s.items():
+    if isinstance(v,dict): print(k, {a:b for a,b in v.items() if a not in ('workload','accuracy_vs_fd','collectives')})
+"
