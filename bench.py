@@ -103,7 +103,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("FPS_BENCH_CLOCK_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -314,7 +314,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+
+        # a collective that waits longer than this is a dead-lock, not a slow rank: fail in minutes, not in NCCL's default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
     from fast_poisson_solver_b200 import Solver, _lib
 
     os.makedirs("/tmp/fps_bench_cwd", exist_ok=True)
@@ -375,7 +378,7 @@ def run_ours(args):
     # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up: its NVML initialisation would
     # otherwise fall into the first timed steps
     clocks = Clocks(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("FPS_BENCH_NO_CLOCKS") != "1":
         clocks.start()
         time.sleep(1.0)
     for _ in range(warm):

@@ -290,7 +290,9 @@ def main():
     torch.cuda.set_device(env.local)
     if env.world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=env.dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=env.dev, timeout=datetime.timedelta(seconds=300))
     os.makedirs("/tmp/fps_bench_cwd", exist_ok=True)
     os.chdir("/tmp/fps_bench_cwd")
     if a.config == "c3":

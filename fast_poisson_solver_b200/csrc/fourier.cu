@@ -62,7 +62,7 @@ __device__ __forceinline__ void store_planes2(const ActPlanes& P, size_t idx, fl
 template <int S>
 __global__ void __launch_bounds__(FOURIER_THREADS)
 fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
-               const double* __restrict__ ffm, const ActPlanes P, const StreamScale sc) {
+               const double* __restrict__ ffm, const ActPlanes P, const StreamScale sc, const int ldk) {
   const int j = 2 * threadIdx.x;
   double f0[2] = {0, 0}, f1[2] = {0, 0}, c[2] = {0, 0}, beta[2] = {0, 0}, k2[2];
   if (j < NFREQ) {
@@ -77,7 +77,7 @@ fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64
 #pragma unroll
   for (int u = 0; u < 2; ++u) k2[u] = f0[u] * f0[u] + f1[u] * f1[u];
   for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
-    const size_t row = (size_t)p * S * K0P;
+    const size_t row = (size_t)p * S * ldk;
     if (j < NFREQ) {
       const double xp = x[p], yp = y[p];
       double sn[2], cs[2];
@@ -90,20 +90,20 @@ fourier_kernel(const double* __restrict__ x, const double* __restrict__ y, int64
       store_planes2(P, row + j, (float)sn[0], (float)sn[1], sc.s[0]);
       store_planes2(P, row + NFREQ + j, (float)cs[0], (float)cs[1], sc.s[0]);
       if (S == 4) {
-        store_planes2(P, row + K0P + j, (float)(cs[0] * f0[0]), (float)(cs[1] * f0[1]), sc.s[1]);
-        store_planes2(P, row + K0P + NFREQ + j, (float)(-sn[0] * f0[0]), (float)(-sn[1] * f0[1]), sc.s[1]);
-        store_planes2(P, row + 2 * K0P + j, (float)(cs[0] * f1[0]), (float)(cs[1] * f1[1]), sc.s[2]);
-        store_planes2(P, row + 2 * K0P + NFREQ + j, (float)(-sn[0] * f1[0]), (float)(-sn[1] * f1[1]), sc.s[2]);
-        store_planes2(P, row + 3 * K0P + j, (float)(-k2[0] * sn[0]), (float)(-k2[1] * sn[1]), sc.s[3]);
-        store_planes2(P, row + 3 * K0P + NFREQ + j, (float)(-k2[0] * cs[0]), (float)(-k2[1] * cs[1]), sc.s[3]);
+        store_planes2(P, row + ldk + j, (float)(cs[0] * f0[0]), (float)(cs[1] * f0[1]), sc.s[1]);
+        store_planes2(P, row + ldk + NFREQ + j, (float)(-sn[0] * f0[0]), (float)(-sn[1] * f0[1]), sc.s[1]);
+        store_planes2(P, row + 2 * ldk + j, (float)(cs[0] * f1[0]), (float)(cs[1] * f1[1]), sc.s[2]);
+        store_planes2(P, row + 2 * ldk + NFREQ + j, (float)(-sn[0] * f1[0]), (float)(-sn[1] * f1[1]), sc.s[2]);
+        store_planes2(P, row + 3 * ldk + j, (float)(-k2[0] * sn[0]), (float)(-k2[1] * sn[1]), sc.s[3]);
+        store_planes2(P, row + 3 * ldk + NFREQ + j, (float)(-k2[0] * cs[0]), (float)(-k2[1] * cs[1]), sc.s[3]);
       }
     } else if (j < NFREQ + 8) {
       // zero the K padding (columns 400..415) of every stream row: 4 threads x 4 columns
       const int c0 = K0 + 2 * (j - NFREQ);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        store_planes2(P, row + s * K0P + c0, 0.f, 0.f, 1.f);
-        store_planes2(P, row + s * K0P + c0 + 2, 0.f, 0.f, 1.f);
+        store_planes2(P, row + s * ldk + c0, 0.f, 0.f, 1.f);
+        store_planes2(P, row + s * ldk + c0 + 2, 0.f, 0.f, 1.f);
       }
     }
   }
@@ -114,9 +114,9 @@ int launch_fourier(const fps_ctx* ctx, const double* x, const double* y, int64_t
   if (n <= 0) return 0;
   int64_t blocks = n < (int64_t)ctx->sm_count * 16 ? n : (int64_t)ctx->sm_count * 16;
   if (streams == 4)
-    fourier_kernel<4><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0]);
+    fourier_kernel<4><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0], ctx->layer[0].ldk);
   else
-    fourier_kernel<1><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0]);
+    fourier_kernel<1><<<(unsigned)blocks, FOURIER_THREADS, 0, st>>>(x, y, n, ctx->ffm, out, ctx->act_scale[0], ctx->layer[0].ldk);
   count_launch();
   FPS_CUDA(cudaGetLastError());
   return 0;

@@ -75,9 +75,9 @@ static int upload_layer_f64(fps_ctx* ctx, int l, const float* w, const float* b,
   return 0;
 }
 
-static int upload_layer(Layer& L, const float* w, const float* b, int cols, int Kp) {
-  std::vector<float> hi((size_t)FPW * Kp, 0.f), lo((size_t)FPW * Kp, 0.f), bias(FPW, 0.f);
-  std::vector<__half> hi16((size_t)FPW * Kp, __float2half(0.f)), lo16((size_t)FPW * Kp, __float2half(0.f));
+static int upload_layer(Layer& L, const float* w, const float* b, int cols, int Kp, int ldk) {
+  std::vector<float> hi((size_t)FPW * ldk, 0.f), lo((size_t)FPW * ldk, 0.f), bias(FPW, 0.f);
+  std::vector<__half> hi16((size_t)FPW * ldk, __float2half(0.f)), lo16((size_t)FPW * ldk, __float2half(0.f));
   for (int r = 0; r < F; ++r) {
     for (int c = 0; c < cols; ++c) {
       const float v = w[(size_t)r * cols + c];
@@ -86,17 +86,18 @@ static int upload_layer(Layer& L, const float* w, const float* b, int cols, int 
       u &= 0xffffe000u;
       float h;
       memcpy(&h, &u, 4);
-      hi[(size_t)r * Kp + c] = h;
-      lo[(size_t)r * Kp + c] = v - h;
+      hi[(size_t)r * ldk + c] = h;
+      lo[(size_t)r * ldk + c] = v - h;
       const float t = v * W16_SCALE;
       const __half th = __float2half_rn(t);
-      hi16[(size_t)r * Kp + c] = th;
-      lo16[(size_t)r * Kp + c] = __float2half_rn(t - __half2float(th));
+      hi16[(size_t)r * ldk + c] = th;
+      lo16[(size_t)r * ldk + c] = __float2half_rn(t - __half2float(th));
     }
     bias[r] = b[r];
   }
   L.Kp = Kp;
-  const size_t bytes = (size_t)FPW * Kp * sizeof(float);
+  L.ldk = ldk;
+  const size_t bytes = (size_t)FPW * ldk * sizeof(float);
   FPS_CUDA(cudaMalloc(&L.w_hi, bytes));
   FPS_CUDA(cudaMalloc(&L.w_lo, bytes));
   FPS_CUDA(cudaMalloc(&L.bias, FPW * sizeof(float)));
@@ -113,11 +114,11 @@ static int upload_layer(Layer& L, const float* w, const float* b, int cols, int 
 // max |v| per stream (row % S) over a (rows x K) hi/lo fp32 plane pair -> out[4] (atomicMax on float bits)
 template <int S>
 __global__ void plane_absmax_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int64_t rows, int K,
-                                    unsigned int* __restrict__ out) {
+                                    int ldk, unsigned int* __restrict__ out) {
   float m[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     float mm = 0.f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) mm = fmaxf(mm, fabsf(hi[r * K + k] + lo[r * K + k]));
+    for (int k = threadIdx.x; k < K; k += blockDim.x) mm = fmaxf(mm, fabsf(hi[r * ldk + k] + lo[r * ldk + k]));
     m[S == 4 ? (int)(r & 3) : 0] = fmaxf(m[S == 4 ? (int)(r & 3) : 0], mm);
   }
 #pragma unroll
@@ -169,8 +170,10 @@ int fps_create(fps_ctx** out, int device, const fps_weights* w, int chunk_points
   // default wave: 296 row tiles x 6 feature tiles = 1776 = 12 x 148 CTA tiles (no tail wave on B200)
   // default wave: 37 888 points (1.7 GB of activation planes); fewer, longer launches than the earlier 18 944
   ctx->chunk = chunk_points > 0 ? (chunk_points + 127) / 128 * 128 : 37888;
-  int rc = upload_layer(ctx->layer[0], w->h_w0, w->h_b0, K0, K0P);
-  for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer(ctx->layer[l + 1], w->h_wh[l], w->h_bh[l], F, FP);
+  int k0ld = getenv("FPS_K0_LD") ? atoi(getenv("FPS_K0_LD")) : K0LD;
+  if (k0ld < K0P || k0ld > FP || k0ld % 8) k0ld = K0LD;     // 16-byte row pitch in every format, inside a plane row
+  int rc = upload_layer(ctx->layer[0], w->h_w0, w->h_b0, K0, K0P, k0ld);
+  for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer(ctx->layer[l + 1], w->h_wh[l], w->h_bh[l], F, FP, FP);
   if (rc == 0) rc = upload_layer_f64(ctx, 0, w->h_w0, w->h_b0, K0, K0P);
   for (int l = 0; l < FPS_NHIDDEN && rc == 0; ++l) rc = upload_layer_f64(ctx, l + 1, w->h_wh[l], w->h_bh[l], F, FP);
   if (rc) { fps_destroy(ctx); return rc; }
@@ -270,7 +273,7 @@ static int cal_forward(fps_ctx* ctx, const double* x, const double* y, int64_t n
     const bool last = l == NLAYER - 1;
     if (d_max) {
       plane_absmax_kernel<4><<<512, 256, 0, st>>>(ctx->act[cur].hi, ctx->act[cur].lo, np * NSTREAM, ctx->layer[l].Kp,
-                                                  d_max + 4 * l);
+                                                  ctx->layer[l].ldk, d_max + 4 * l);
       count_launch();
     }
     rc = (engine == FPS_ENGINE_TCGEN05)

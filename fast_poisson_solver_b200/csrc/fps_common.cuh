@@ -17,6 +17,11 @@ constexpr int FP = FPS_FP;        // padded feature dimension (row stride of eve
 constexpr int FPW = 768;          // weight rows padded to 6 x 128 (UMMA M tiles); rows >= F are zero
 constexpr int K0 = FPS_K0;        // 400 Fourier inputs
 constexpr int K0P = 416;          // K0 padded to a multiple of 32 (one 128-byte TMA/UMMA K-chunk)
+// Row pitch (elements) of the first layer's operand planes - Fourier activations and W0 alike.  416 halves are 832 bytes:
+// every other row would start in the middle of a 128-byte line and each 128-byte slab row of a TMA box would touch two L2
+// lines.  448 halves = 7 x 128 bytes keeps every slab row inside one line; columns 416..447 are never written nor read
+// (the tensor maps end at K0P and zero-fill beyond).  FPS_K0_LD overrides (A/B measurements).
+constexpr int K0LD = 448;
 constexpr int NFREQ = FPS_NFREQ;  // 200
 constexpr int NLAYER = 1 + FPS_NHIDDEN;  // mapping.linear + 5 hidden
 constexpr int NSTREAM = 4;        // value, d/dx, d/dy, laplacian
@@ -51,6 +56,7 @@ struct Layer {
   __half* w_hi16;  // (FPW, Kp) fp16(w * W16_SCALE)
   __half* w_lo16;  // (FPW, Kp) fp16(w * W16_SCALE - w_hi16)
   int Kp;        // padded K (K0P for layer 0, FP otherwise)
+  int ldk;       // row pitch in elements of the weight planes AND of this layer's input planes (K0LD for layer 0, else FP)
 };
 
 struct StreamScale {  // per-stream power-of-two scales of one layer's input planes (f16 format)

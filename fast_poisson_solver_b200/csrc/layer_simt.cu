@@ -16,7 +16,7 @@ constexpr int SBM = 128, SBN = 64, SBK = 16, STHREADS = 256;
 
 template <int S, bool LAST>
 __global__ void __launch_bounds__(STHREADS)
-layer_simt_kernel(const ActPlanes in, const StreamScale in_sc, int Kp,
+layer_simt_kernel(const ActPlanes in, const StreamScale in_sc, int Kp, int ldk,
                   const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
                   const ActPlanes outp, const StreamScale out_sc, float* __restrict__ H,
                   float* __restrict__ DH, int64_t ld, int64_t rows) {
@@ -38,16 +38,16 @@ layer_simt_kernel(const ActPlanes in, const StreamScale in_sc, int Kp,
   const int a_row = t / 2, a_k = (t % 2) * 8;
   const int b_row = t / 4, b_k = (t % 4) * 4;
   const bool a_ok = row0 + a_row < rows;
-  const float* a_hi = in_hi + (row0 + a_row) * Kp + a_k;
-  const float* a_lo = in_lo + (row0 + a_row) * Kp + a_k;
-  const float* b_hi = w_hi + (size_t)(col0 + b_row) * Kp + b_k;
-  const float* b_lo = w_lo + (size_t)(col0 + b_row) * Kp + b_k;
+  const float* a_hi = in_hi + (row0 + a_row) * ldk + a_k;
+  const float* a_lo = in_lo + (row0 + a_row) * ldk + a_k;
+  const float* b_hi = w_hi + (size_t)(col0 + b_row) * ldk + b_k;
+  const float* b_lo = w_lo + (size_t)(col0 + b_row) * ldk + b_k;
 
   for (int k0 = 0; k0 < Kp; k0 += SBK) {
     float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
     if (a_ok && in.f16) {
       // FP16x2-split planes: value = (hi16 + lo16) / scale[stream of this row]
-      const size_t base = (size_t)(row0 + a_row) * Kp + a_k + k0;
+      const size_t base = (size_t)(row0 + a_row) * ldk + a_k + k0;
       const float inv = 1.0f / in_sc.s[S == 4 ? (int)((row0 + a_row) & 3) : 0];
       const uint4 qh = *reinterpret_cast<const uint4*>(in.hi16 + base);
       const uint4 ql = *reinterpret_cast<const uint4*>(in.lo16 + base);
@@ -142,7 +142,7 @@ int launch_layer_simt(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, in
   const int64_t rows = points * streams;
   dim3 grid((unsigned)((rows + SBM - 1) / SBM), FP / SBN);
 #define FPS_SIMT_LAUNCH(S_, LAST_)                                                                           \
-  layer_simt_kernel<S_, LAST_><<<grid, STHREADS, 0, st>>>(in, ctx->act_scale[l], L.Kp, L.w_hi, L.w_lo, L.bias, out, \
+  layer_simt_kernel<S_, LAST_><<<grid, STHREADS, 0, st>>>(in, ctx->act_scale[l], L.Kp, L.ldk, L.w_hi, L.w_lo, L.bias, out, \
                                                            ctx->act_scale[l + 1 < NLAYER ? l + 1 : l], H, DH, ld, rows)
   if (streams == 4) {
     if (last) FPS_SIMT_LAUNCH(4, true); else FPS_SIMT_LAUNCH(4, false);

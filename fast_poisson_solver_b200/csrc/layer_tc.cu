@@ -25,7 +25,7 @@
 //
 // Accumulation accuracy.  The tensor core truncates (rounds toward zero) when it writes the fp32
 // accumulator, so a single 704-long chain biases every output by ~3e-6 per layer (measured: H off by 1.6e-5
-// after six layers).  The K loop is therefore cut into segments (K = 192): each segment accumulates in TMEM
+// after six layers).  The K loop is therefore cut into segments (K = 192 or 256): each segment accumulates in TMEM
 // from zero, then the accumulate warps pull it out with tcgen05.ld and add it, times a gain 1 + kappa(K_seg)
 // that compensates the first-order shrink, to a round-to-nearest fp32 running sum held in registers while the
 // tensor core already works on the next segment in the other TMEM buffer.
@@ -515,11 +515,11 @@ struct TcState {
 
 // 2-D K-major map: dims {K, rows}, box {rb bytes of K, 128 rows}, swizzle span = rb (64: 16 floats or 32 halves
 // per row; 128: 64 halves per row).  A box that overhangs K (K0P = 416 with 64-wide slabs) is zero-filled.
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t K, uint64_t rows, bool half,
-                    int rb = 64) {
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, uint64_t K, uint64_t pitch, uint64_t rows,
+                    bool half, int rb = 64) {
   const uint64_t esz = half ? 2 : 4;
   cuuint64_t dims[2] = {K, rows};
-  cuuint64_t strides[1] = {K * esz};
+  cuuint64_t strides[1] = {pitch * esz};   // pitch >= K: columns K.. of a row are never fetched (zero fill)
   cuuint32_t box[2] = {(cuuint32_t)(rb / esz), (cuuint32_t)BOX_ROWS};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
@@ -565,25 +565,26 @@ int tc_init(fps_ctx* ctx) {
   FPS_REQUIRE(s->rb == 64 || s->rb == 128, "FPS_TC_ROWB must be 64 or 128");
   for (int l = 0; l < NLAYER; ++l) {
     const Layer& L = ctx->layer[l];
-    if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, FPW, false)) return 1;
-    if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, FPW, false)) return 1;
-    if (make_map(enc, &s->w_hi16[l], L.w_hi16, L.Kp, FPW, true)) return 1;
-    if (make_map(enc, &s->w_lo16[l], L.w_lo16, L.Kp, FPW, true)) return 1;
-    if (make_map(enc, &s->w_hi16w[l], L.w_hi16, L.Kp, FPW, true, 128)) return 1;
-    if (make_map(enc, &s->w_lo16w[l], L.w_lo16, L.Kp, FPW, true, 128)) return 1;
+    if (make_map(enc, &s->w_hi[l], L.w_hi, L.Kp, L.ldk, FPW, false)) return 1;
+    if (make_map(enc, &s->w_lo[l], L.w_lo, L.Kp, L.ldk, FPW, false)) return 1;
+    if (make_map(enc, &s->w_hi16[l], L.w_hi16, L.Kp, L.ldk, FPW, true)) return 1;
+    if (make_map(enc, &s->w_lo16[l], L.w_lo16, L.Kp, L.ldk, FPW, true)) return 1;
+    if (make_map(enc, &s->w_hi16w[l], L.w_hi16, L.Kp, L.ldk, FPW, true, 128)) return 1;
+    if (make_map(enc, &s->w_lo16w[l], L.w_lo16, L.Kp, L.ldk, FPW, true, 128)) return 1;
   }
   const uint64_t cap_rows = (uint64_t)ctx->chunk * NSTREAM;
   for (int b = 0; b < 2; ++b) {
     // a plane holds cap_rows x FP elements; viewed with K = K0P it has room for more rows, but the same
     // row capacity is all a wave ever uses
     const uint64_t Ks[2] = {(uint64_t)K0P, (uint64_t)FP};
+    const uint64_t Ls[2] = {(uint64_t)ctx->layer[0].ldk, (uint64_t)FP};
     for (int kv = 0; kv < 2; ++kv) {
-      if (make_map(enc, &s->act_hi[b][kv], ctx->act[b].hi, Ks[kv], cap_rows, false)) return 1;
-      if (make_map(enc, &s->act_lo[b][kv], ctx->act[b].lo, Ks[kv], cap_rows, false)) return 1;
-      if (make_map(enc, &s->act_hi16[b][kv], ctx->act[b].hi16, Ks[kv], cap_rows, true)) return 1;
-      if (make_map(enc, &s->act_lo16[b][kv], ctx->act[b].lo16, Ks[kv], cap_rows, true)) return 1;
-      if (make_map(enc, &s->act_hi16w[b][kv], ctx->act[b].hi16, Ks[kv], cap_rows, true, 128)) return 1;
-      if (make_map(enc, &s->act_lo16w[b][kv], ctx->act[b].lo16, Ks[kv], cap_rows, true, 128)) return 1;
+      if (make_map(enc, &s->act_hi[b][kv], ctx->act[b].hi, Ks[kv], Ls[kv], cap_rows, false)) return 1;
+      if (make_map(enc, &s->act_lo[b][kv], ctx->act[b].lo, Ks[kv], Ls[kv], cap_rows, false)) return 1;
+      if (make_map(enc, &s->act_hi16[b][kv], ctx->act[b].hi16, Ks[kv], Ls[kv], cap_rows, true)) return 1;
+      if (make_map(enc, &s->act_lo16[b][kv], ctx->act[b].lo16, Ks[kv], Ls[kv], cap_rows, true)) return 1;
+      if (make_map(enc, &s->act_hi16w[b][kv], ctx->act[b].hi16, Ks[kv], Ls[kv], cap_rows, true, 128)) return 1;
+      if (make_map(enc, &s->act_lo16w[b][kv], ctx->act[b].lo16, Ks[kv], Ls[kv], cap_rows, true, 128)) return 1;
     }
   }
   if (set_smem_all<false>() || set_smem_all<true>() || set_smem_wide()) return 1;
@@ -658,14 +659,29 @@ int launch_layer_tc(const fps_ctx* ctx, int l, ActPlanes in, ActPlanes out, int6
   P.row_tiles = (int)((P.rows + TN - 1) / TN);
   static const int stats = getenv("FPS_TC_STATS") ? atoi(getenv("FPS_TC_STATS")) : 0;
   P.stats = stats;
+  // K slabs per tensor-core accumulation segment.  3xTF32: 128.  FP16x2 (64-wide slabs): hidden layers 3 = segments of
+  // 192, 192, 192, 128 per K = 704; first and last layer 4 = 256, 160 resp. 256, 256, 192.  The MMA issuer may run two
+  // segments ahead of the accumulate warps (two TMEM buffers), and those warps spend ~8.2 K cycles per tile in the
+  // epilogue before they drain the next tile's first segment: with 192-wide segments the look-ahead (9.2 K cycles of
+  // MMAs) falls short of epilogue + drains in the last layer (fused digit split) and the first one (K = 416), and the
+  // tensor pipe idles; 256-wide segments cover it (measured, interleaved runs under the power cap: last layer 1.084 ->
+  // 0.972 of a hidden layer's time, first layer 0.185 -> 0.174 of the four hidden ones).  The hidden layers gain nothing
+  // from longer segments and keep 192, because the truncation bias of a segment grows with its length: H / DH vs fp64
+  // 6.98e-7 / 1.09e-6 (all 192), 7.44e-7 / 1.12e-6 (this mix; the fp32 FFMA engine: 7.3e-7 / 1.1e-6), 8.16e-7 / 1.22e-6
+  // (all 256).  FPS_TC_SEG (all layers) / FPS_TC_SEG_L0 / _HID / _LAST override (measurements).
   static const int seg_env = getenv("FPS_TC_SEG") ? atoi(getenv("FPS_TC_SEG")) : 0;
-  // K per tensor-core accumulation segment: 192 (FP16x2: 3 segments + a 128 tail per 704) or 128 (3xTF32)
-  const int seg = seg_env ? seg_env : (f16 ? 192 : 128) / slab_k;
+  static const int seg_env_l0 = getenv("FPS_TC_SEG_L0") ? atoi(getenv("FPS_TC_SEG_L0")) : 0;
+  static const int seg_env_hid = getenv("FPS_TC_SEG_HID") ? atoi(getenv("FPS_TC_SEG_HID")) : 0;
+  static const int seg_env_last = getenv("FPS_TC_SEG_LAST") ? atoi(getenv("FPS_TC_SEG_LAST")) : 0;
+  const int seg_layer = (l == 0) ? seg_env_l0 : (last ? seg_env_last : seg_env_hid);
+  const int seg_default = f16 ? ((l == 0 || last) ? 256 : 192) / slab_k : 128 / slab_k;
+  const int seg = seg_layer ? seg_layer : seg_env ? seg_env : seg_default;
   P.seg = seg;
   static const char* kenv = getenv("FPS_TC_KAPPA");
   const int tail = (P.nk % seg) ? (P.nk % seg) : seg;
   P.gain = 1.0f + (kenv ? (float)atof(kenv) : kappa_of(seg * slab_k, f16));
-  P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail * slab_k, f16));
+  const int tail_k = L.Kp - (P.nk - tail) * slab_k;   // real K of the last segment (the zero-filled MMA steps are skipped)
+  P.gain_tail = 1.0f + (kenv ? (float)atof(kenv) * powf((float)tail / seg, 0.55f) : kappa_of(tail_k, f16));
   if (ctx->gain_off) P.gain = P.gain_tail = 1.0f;   // fps_calibrate_scales found the compensation harmful for these weights
   const int ncta = s->pair ? 2 : 1;
   {

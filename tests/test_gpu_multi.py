@@ -16,7 +16,10 @@ def _worker(rank, world, port, G, B, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import datetime
+
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
     try:
         from fast_poisson_solver_b200 import Solver
         from fast_poisson_solver_b200.parallel import shard_bounds
