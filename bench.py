@@ -288,15 +288,18 @@ def multi_gpu_parity(torch, dist, world, rank, local):
     if rank == 0:
         full = torch.cat([g[:n] for g, n in zip(gathered, sizes)], dim=0).double()
         ref = Solver(device=f"cuda:{local}", use_weights=False)
+        # the calibration (fp16 operand scales, fixed-point grid of DH) belongs to the problem: the sharded run combined
+        # it over the ranks, the single-GPU run takes the same state -> bit-identical features on both sides
+        ref.set_calibration(s.calibration_state())
         ref.precompute(xp, yp, xb, yb)
         r_pde = ref.solve(Fm, bcv)[1].double()
         r1 = ref.solve(Fm[:, 1], np.full(xb.size, bcv[1]))[1].double()
         eb = max(float((full[:, j] - r_pde[:, j]).norm() / r_pde[:, j].norm()) for j in range(B))
         e1 = float((full[:, B] - r1[:, 0]).norm() / r1[:, 0].norm())
         out = {"points": int(xp.size), "rhs": B, "ranks": world, "worst_u_rel_l2_batched": eb, "u_rel_l2_single": e1,
-               "tolerance": 5e-6, "pass": bool(eb < 5e-6 and e1 < 5e-6),
-               "note": "same kernels and features; the summation order of the fp64 partial Grams / projections differs and "
-                       "every rank snaps its rows of DH to its own calibrated grid"}
+               "tolerance": 1e-6, "pass": bool(eb < 1e-6 and e1 < 1e-6),
+               "note": "same kernels, same calibration state (combined over the ranks with one small all-reduce), hence "
+                       "bit-identical features; what differs is the summation order of the fp64 partial Grams / projections"}
         del ref
     del s
     torch.cuda.empty_cache()

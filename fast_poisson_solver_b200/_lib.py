@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libfps_sm100.so")
 
 F = 700
 FP = 704
+FPW = 768  # weight / plane rows: 6 UMMA tiles of 128 features
 LROWS = 1440  # FPS_LROWS: factor buffer rows (L + diagonal-block inverses + explicit inverse)
 K0 = 400
 NFREQ = 200
@@ -49,6 +50,8 @@ SIGNATURES = {
     "fps_get_scales": (_i32, [_vp, C.POINTER(C.c_float)]),
     "fps_set_calibration": (_i32, [_vp, C.POINTER(C.c_float), _i32]),
     "fps_get_calibration": (_i32, [_vp, C.POINTER(_f64)]),
+    "fps_get_dh_calibration": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "fps_set_dh_calibration": (_i32, [_vp, C.POINTER(C.c_float)]),
     "fps_workspace_bytes": (C.c_size_t, [_vp]),
     "fps_features": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "fps_gram_accum": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),

@@ -377,6 +377,29 @@ int fps_set_calibration(fps_ctx* ctx, const float* in24, int gain_on) {
   return 0;
 }
 
+int fps_get_dh_calibration(const fps_ctx* ctx, float* h_out) {
+  FPS_REQUIRE(ctx && h_out, "fps_get_dh_calibration: null argument");
+  if (!ctx->dh_cal_valid) {
+    for (int i = 0; i < FPW; ++i) h_out[i] = 0.f;
+    return 0;
+  }
+  // (the maxima are non-negative floats stored as their bit patterns; the copy synchronises the device)
+  FPS_CUDA(cudaMemcpy(h_out, ctx->dh_cal_cmax, FPW * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int fps_set_dh_calibration(fps_ctx* ctx, const float* h_in) {
+  FPS_REQUIRE(ctx && h_in, "fps_set_dh_calibration: null argument");
+  bool any = false;
+  for (int i = 0; i < FPW; ++i) {
+    FPS_REQUIRE(h_in[i] >= 0.f && h_in[i] < 3.0e38f, "fps_set_dh_calibration: maximum %d is negative or not finite", i);
+    any = any || h_in[i] > 0.f;
+  }
+  FPS_CUDA(cudaMemcpy(ctx->dh_cal_cmax, h_in, FPW * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->dh_cal_valid = any ? 1 : 0;
+  return 0;
+}
+
 int fps_set_engine(fps_ctx* ctx, int engine) {
   FPS_REQUIRE(ctx, "null ctx");
   FPS_REQUIRE(engine == FPS_ENGINE_SIMT || engine == FPS_ENGINE_TCGEN05, "unknown engine %d", engine);

@@ -158,6 +158,7 @@ class Solver:
         # at most a quarter of the free device memory; FPS_CACHE_PLANES=0/1 or cache_planes=False/True force it)
         env = os.environ.get("FPS_CACHE_PLANES")
         self._cache_planes = cache_planes if cache_planes is not None else (None if env is None else env != "0")
+        self._fixed_cal = None      # a calibration state imposed by set_calibration() (None: measured per precompute)
         self._exact_min = int(self._lib.fps_exact_min_rows())
         self._reserved = (0, 0)
         self._comm = None
@@ -324,17 +325,59 @@ class Solver:
 
     def _calibrate(self, x64):
         """Fit the fp16 operand scales of the tensor-core engine (and the fixed-point grid of DH) to this network /
-        domain on an evenly strided sample of 512 collocation points (grids come sorted)."""
-        if self._fdtype != torch.float32 or not x64[0].numel():
+        domain on an evenly strided sample of 512 collocation points (grids come sorted).  With `distributed=True` the
+        states of all ranks are combined (one small all-reduce): the calibration belongs to the problem, not to the
+        shard, so a point's features do not depend on the rank it was assigned to."""
+        if self._fdtype != torch.float32:
+            return
+        if self._fixed_cal is not None:
+            self._apply_calibration(self._fixed_cal)
             return
         n_all = x64[0].numel()
-        if n_all > 512:
-            pick = torch.linspace(0, n_all - 1, 512, device=self._tdev).long()
-            xs, ys = x64[0][pick].contiguous(), x64[1][pick].contiguous()
-        else:
-            xs, ys = x64[0], x64[1]
-        _lib.check(self._lib.fps_calibrate_scales(self._ctx, xs.data_ptr(), ys.data_ptr(), xs.numel(), self._stream()),
-                   "fps_calibrate_scales")
+        if n_all:
+            if n_all > 512:
+                pick = torch.linspace(0, n_all - 1, 512, device=self._tdev).long()
+                xs, ys = x64[0][pick].contiguous(), x64[1][pick].contiguous()
+            else:
+                xs, ys = x64[0], x64[1]
+            _lib.check(self._lib.fps_calibrate_scales(self._ctx, xs.data_ptr(), ys.data_ptr(), xs.numel(), self._stream()),
+                       "fps_calibrate_scales")
+        if self.distributed:
+            import torch.distributed as dist
+
+            # MIN of the power-of-two scales and of the gain switch, MAX of the DH maxima, as ONE max-reduction of
+            # [-scales | -gain_on | dh maxima]; a rank without points contributes the neutral element
+            st = self.calibration_state() if n_all else {"scales": [3.0e38] * 24, "gain_on": -1, "dh_cmax": np.zeros(_lib.FPW)}
+            keep_gain = 0.0 if st["gain_on"] == 0 else 1.0          # switched off as soon as one rank found it harmful
+            v = np.concatenate([-np.asarray(st["scales"], dtype=np.float64), [-keep_gain],
+                                np.asarray(st["dh_cmax"], dtype=np.float64)])
+            t = torch.as_tensor(v, device=self._tdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.process_group)
+            v = t.cpu().numpy()
+            if -v[0] < 1.0e38:      # at least one rank had points
+                gain = 0 if -v[24] < 0.5 else (1 if st["gain_on"] >= 0 else -1)
+                self._apply_calibration({"scales": (-v[:24]).tolist(), "gain_on": gain, "dh_cmax": v[25:]})
+
+    def calibration_state(self):
+        """The calibration the last precompute ran with: 6 x 4 power-of-two operand scales (layer input x stream), the
+        accumulator-gain switch (1 / 0; -1 = not checked) and max |DH| per feature (768 floats, zero = none)."""
+        sc, cal, dh = (C.c_float * 24)(), (C.c_double * 5)(), (C.c_float * _lib.FPW)()
+        _lib.check(self._lib.fps_get_scales(self._ctx, sc), "fps_get_scales")
+        _lib.check(self._lib.fps_get_calibration(self._ctx, cal), "fps_get_calibration")
+        _lib.check(self._lib.fps_get_dh_calibration(self._ctx, dh), "fps_get_dh_calibration")
+        return {"scales": [float(v) for v in sc], "gain_on": int(cal[4]), "dh_cmax": np.array(dh, dtype=np.float32)}
+
+    def set_calibration(self, state):
+        """Impose a calibration state (from `calibration_state()` of another Solver) on every later precompute instead of
+        measuring one; None returns to measuring.  Two Solvers with the same weights and the same calibration produce
+        bit-identical features for the same point (e.g. a single-GPU run checked against a sharded one)."""
+        self._fixed_cal = state
+
+    def _apply_calibration(self, state):
+        sc = (C.c_float * 24)(*[float(v) for v in state["scales"]])
+        _lib.check(self._lib.fps_set_calibration(self._ctx, sc, int(state.get("gain_on", -1))), "fps_set_calibration")
+        dh = (C.c_float * _lib.FPW)(*[float(v) for v in np.asarray(state["dh_cmax"], dtype=np.float32)])
+        _lib.check(self._lib.fps_set_dh_calibration(self._ctx, dh), "fps_set_dh_calibration")
 
     def _compute(self, x64):
         self._refactor_pending = False

@@ -84,6 +84,13 @@ int fps_set_calibration(fps_ctx* ctx, const float* h_in24, int gain_on);
  * fps_get_calibration: h_out5 = {rel-L2 of H, DH vs the fp32 engine with the compensation, the same without,
  * 1 = compensation in use / 0 = switched off / -1 = not checked yet}.                                               */
 int fps_get_calibration(const fps_ctx* ctx, double* h_out5);
+/* The calibrated maxima of |DH| per feature (host float[768], rows 704.. are zero; all zero = not calibrated).  Together
+ * with fps_get_scales / fps_set_calibration this is the whole calibration state: a caller that shards the points over
+ * several contexts (GPUs) combines the states (minimum of the scales, maximum of the maxima) and sets the result in
+ * every context, so that a point's features do not depend on which shard it fell into (fast_poisson_solver_b200/
+ * solver.py does this with one small all-reduce per precompute).  Both calls synchronise the device.                 */
+int fps_get_dh_calibration(const fps_ctx* ctx, float* h_out768);
+int fps_set_dh_calibration(fps_ctx* ctx, const float* h_in768);
 int fps_get_engine(const fps_ctx* ctx);
 size_t fps_workspace_bytes(const fps_ctx* ctx);
 

@@ -1,4 +1,5 @@
-"""GPU, >= 2 devices: row-sharded precompute + solve over NCCL against the single-GPU result."""
+"""Row-sharded precompute + solve against the single-GPU result: over NCCL with one rank per device (>= 2 devices), and
+with 8 ranks sharing ONE device over gloo (the same host logic and kernels; runs on a single-GPU box as well)."""
 import os
 
 import numpy as np
@@ -10,16 +11,23 @@ from oracle import fps_oracle as o
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, G, B, out_dir):
+def _worker(rank, world, port, G, B, out_dir, shared_gpu=False):
+    import datetime
+
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    import datetime
-
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
-                            timeout=datetime.timedelta(seconds=120))
+    dev = 0 if shared_gpu else rank
+    torch.cuda.set_device(dev)
+    if shared_gpu:
+        # NCCL cannot place two ranks on one device: gloo carries the same all-reduces (FPS_COMM=torch keeps the
+        # library's own NCCL communicator out of the way)
+        os.environ["FPS_COMM"] = "torch"
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                                timeout=datetime.timedelta(seconds=120))
     try:
         from fast_poisson_solver_b200 import Solver
         from fast_poisson_solver_b200.parallel import shard_bounds
@@ -30,15 +38,49 @@ def _worker(rank, world, port, G, B, out_dir):
         blo, bhi = shard_bounds(xb.size, rank, world)
         Fm = np.stack([(50.0 + j) * np.sin((2 + j % 4) * np.pi * xp) * np.sin((3 + (j // 4) % 3) * np.pi * yp) for j in range(B)], 1)
         bcv = np.linspace(-2, 3, B)
-        s = Solver(device=f"cuda:{rank}", use_weights=False, distributed=True)
+        s = Solver(device=f"cuda:{dev}", use_weights=False, distributed=True)
         s.precompute(xp[lo:hi], yp[lo:hi], xb[blo:bhi], yb[blo:bhi])
         assert s.NO == xp.size and s.NdO == xb.size
         u, u_pde, u_bc, f_pred, _ = s.solve(Fm[lo:hi], np.tile(bcv[None], (bhi - blo, 1)))
         u1 = s.solve(Fm[lo:hi, 0], np.full(bhi - blo, bcv[0]))[1]
+        cal = s.calibration_state()      # combined over the ranks: identical everywhere
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), u_pde=u_pde.cpu().numpy(), u_bc=u_bc.cpu().numpy(),
-                 u1=u1.cpu().numpy())
+                 u1=u1.cpu().numpy(), scales=np.asarray(cal["scales"]), gain_on=cal["gain_on"], dh_cmax=cal["dh_cmax"])
     finally:
         dist.destroy_process_group()
+
+
+def _check_against_single_gpu(tmp_path, world, G, B, tol):
+    from fast_poisson_solver_b200 import Solver
+
+    xp, yp, xb, yb = o.grid_problem(G)
+    Fm = np.stack([(50.0 + j) * np.sin((2 + j % 4) * np.pi * xp) * np.sin((3 + (j // 4) % 3) * np.pi * yp) for j in range(B)], 1)
+    bcv = np.linspace(-2, 3, B)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for p in parts[1:]:          # every rank ended up with the same calibration
+        assert np.array_equal(p["scales"], parts[0]["scales"]) and np.array_equal(p["dh_cmax"], parts[0]["dh_cmax"])
+        assert int(p["gain_on"]) == int(parts[0]["gain_on"])
+    s = Solver(use_weights=False)
+    # the calibration belongs to the problem: with the sharded run's state the single-GPU features are bit-identical,
+    # what remains is the summation order of the fp64 partial Grams / projections
+    s.set_calibration({"scales": parts[0]["scales"], "gain_on": int(parts[0]["gain_on"]), "dh_cmax": parts[0]["dh_cmax"]})
+    s.precompute(xp, yp, xb, yb)
+    u, u_pde, u_bc, _, _ = s.solve(Fm, bcv)
+    up = np.concatenate([p["u_pde"] for p in parts])
+    ub = np.concatenate([p["u_bc"] for p in parts])
+    errs = (o.rel_l2(up, u_pde.cpu().numpy()), o.rel_l2(ub, u_bc.cpu().numpy()),
+            o.rel_l2(np.concatenate([p["u1"] for p in parts]), u_pde[:, [0]].cpu().numpy()))
+    print(f"world {world} G {G} B {B}: u_pde {errs[0]:.2e} u_bc {errs[1]:.2e} single {errs[2]:.2e}")
+    assert max(errs) < tol, errs
+
+
+@pytest.mark.parametrize("world,G,B", [(8, 407, 40)])   # 20 706 points per rank: the exact int8 paths on every rank,
+def test_eight_ranks_on_one_gpu_match_single_solver(tmp_path, world, G, B):   # the sizes of bench.py's parity block
+    import torch.multiprocessing as mp
+
+    port = 29800 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, G, B, str(tmp_path), True), nprocs=world, join=True)
+    _check_against_single_gpu(tmp_path, world, G, B, 1e-6)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
@@ -46,21 +88,7 @@ def _worker(rank, world, port, G, B, out_dir):
 @pytest.mark.parametrize("G,B", [(48, 5), (192, 40)])   # (192, 40): 18 432 points per rank -> the exact int8 Gram /
 def test_row_sharded_matches_single_gpu(tmp_path, world, G, B):   # projection / reconstruction paths on every rank
     import torch.multiprocessing as mp
-    from fast_poisson_solver_b200 import Solver
 
     port = 29600 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, G, B, str(tmp_path)), nprocs=world, join=True)
-    xp, yp, xb, yb = o.grid_problem(G)
-    Fm = np.stack([(50.0 + j) * np.sin((2 + j % 4) * np.pi * xp) * np.sin((3 + (j // 4) % 3) * np.pi * yp) for j in range(B)], 1)
-    bcv = np.linspace(-2, 3, B)
-    s = Solver(use_weights=False)
-    s.precompute(xp, yp, xb, yb)
-    u, u_pde, u_bc, _, _ = s.solve(Fm, bcv)
-    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
-    up = np.concatenate([p["u_pde"] for p in parts])
-    ub = np.concatenate([p["u_bc"] for p in parts])
-    # same kernels, same features; the summation order of the Gram / projection differs (fp64) and, on the int8 path,
-    # every rank snaps its rows of DH to the grid of its own column maxima (2^-31 of the maximum)
-    assert o.rel_l2(up, u_pde.cpu().numpy()) < 1e-6
-    assert o.rel_l2(ub, u_bc.cpu().numpy()) < 1e-6
-    assert o.rel_l2(np.concatenate([p["u1"] for p in parts]), u_pde[:, [0]].cpu().numpy()) < 1e-6
+    _check_against_single_gpu(tmp_path, world, G, B, 1e-6)
