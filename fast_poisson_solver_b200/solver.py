@@ -158,6 +158,7 @@ class Solver:
         # at most a quarter of the free device memory; FPS_CACHE_PLANES=0/1 or cache_planes=False/True force it)
         env = os.environ.get("FPS_CACHE_PLANES")
         self._cache_planes = cache_planes if cache_planes is not None else (None if env is None else env != "0")
+        self._cache_ok_bytes = None
         self._fixed_cal = None      # a calibration state imposed by set_calibration() (None: measured per precompute)
         self._exact_min = int(self._lib.fps_exact_min_rows())
         self._reserved = (0, 0)
@@ -200,9 +201,16 @@ class Solver:
     def _want_cache(self, nbytes):
         if self._cache_planes is not None:
             return bool(self._cache_planes)
+        # cudaMemGetInfo costs ~0.3 ms (measured: the largest idle gap of a step), so a positive answer for a size is
+        # remembered; if memory got scarce since, the allocation itself fails and the caller falls back
+        if self._cache_ok_bytes is not None and nbytes <= self._cache_ok_bytes:
+            return True
         free, _ = torch.cuda.mem_get_info(self._dev_index)
         free += torch.cuda.memory_reserved(self._dev_index) - torch.cuda.memory_allocated(self._dev_index)
-        return nbytes <= free // 4
+        ok = nbytes <= free // 4
+        if ok:
+            self._cache_ok_bytes = nbytes
+        return ok
 
     def _alloc_planes(self, nbytes):
         try:
