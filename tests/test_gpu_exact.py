@@ -441,3 +441,32 @@ def test_accumulator_gain_check_on_other_weight_distributions(make_solver):
         assert cal[4] in (0.0, 1.0)
         assert eh < 1e-5 and ed < 1e-5
         assert min(cal[1], cal[3]) < 1e-5
+
+
+def test_calibration_state_makes_features_independent_of_the_shard(make_solver):
+    """The calibration (fp16 operand scales, gain switch, fixed-point grid of DH) is problem state: a Solver that is handed
+    the state of another one (`calibration_state()` -> `set_calibration()`; C ABI fps_get_scales / fps_set_calibration /
+    fps_get/set_dh_calibration) produces bit-identical H and DH for the same points, wherever they sit in its own point
+    set - the property the multi-GPU path relies on (tests/test_gpu_multi.py).  Without the shared state the two
+    calibrations come from different samples and the features differ in their rounding."""
+    rng = np.random.default_rng(5)
+    n = 60000
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    xb, yb = np.linspace(0, 1, 300), np.zeros(300)
+    a = make_solver()
+    a.precompute(x, y, xb, yb)
+    st = a.calibration_state()
+    assert len(st["scales"]) == 24 and st["gain_on"] in (0, 1) and st["dh_cmax"].shape == (768,)
+    assert (st["dh_cmax"][:700] > 0).all() and (st["dh_cmax"][704:] == 0).all()
+    lo, hi = 10007, 33333                               # a shard that starts in the middle of a tile
+    b = make_solver()
+    b.set_calibration(st)
+    b.precompute(x[lo:hi], y[lo:hi], xb, yb)
+    assert torch.equal(b._Hp, a._Hp[lo:hi]) and torch.equal(b._DHp, a._DHp[lo:hi])
+    st_b = b.calibration_state()
+    assert st_b["scales"] == st["scales"] and np.array_equal(st_b["dh_cmax"], st["dh_cmax"])
+    # back to measuring: the state now comes from the shard's own sample
+    b.set_calibration(None)
+    b.precompute(x[lo:hi], y[lo:hi], xb, yb)
+    assert not np.array_equal(b.calibration_state()["dh_cmax"], st["dh_cmax"])
+    assert o.rel_l2(b._Hp.cpu().numpy(), a._Hp[lo:hi].cpu().numpy()) < 5e-6
