@@ -251,13 +251,14 @@ def ncu_traffic(capture, points_per_launch=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
     capture of this round (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py), scaled to the points one launch
     of THIS run covers; None when no capture is committed."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
-        for k, v in t["bytes_per_launch"].items():
-            if k.startswith(capture + ":"):
-                return v * (points_per_launch / t["points_per_layer_launch"] if points_per_launch else 1.0)
-    except Exception:
-        pass
+    for tag in ("r02b", "r02"):            # r02b: re-capture of the layer kernel after the segment / pitch changes
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic.json")))
+            for k, v in t["bytes_per_launch"].items():
+                if k.startswith(capture + ":"):
+                    return v * (points_per_launch / t["points_per_layer_launch"] if points_per_launch else 1.0)
+        except Exception:
+            pass
     return None
 
 
@@ -530,7 +531,7 @@ def run_ours(args):
                      "points_per_launch": 4 * args.steps * n_pts / hid_n if hid_n else None,
                      "traffic": ncu_traffic("hidden", 4 * args.steps * n_pts / hid_n if hid_n else None),
                      "traffic_unit": "bytes/launch: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                     "(profiles/r02_ncu_traffic.json); null = no capture committed for this build"},
+                                     "(profiles/r02b_ncu_traffic.json); null = no capture committed for this build"},
         "int8_peak": i8,
         "other_rooflines": {
             "features_all_layers": {"achieved": n_pts * FLOP_PER_POINT_FEATURES / (feat_ms * 1e-3) / 1e12,
