@@ -14,7 +14,7 @@ rng = np.random.default_rng(0)
 x = torch.tensor(rng.uniform(0, 1, n), device="cuda"); y = torch.tensor(rng.uniform(0, 1, n), device="cuda")
 g = np.linspace(0, 1, 402)
 xb = torch.tensor(np.concatenate([g, g]), device="cuda"); yb = torch.tensor(np.concatenate([0 * g, 0 * g + 1]), device="cuda")
-s = Solver(use_weights=False)
+s = Solver(use_weights=False, chunk_points=int(os.environ.get("CHUNK", "0")))
 for _ in range(2):
     s.precompute(x, y, xb, yb)           # the production path: fused digit split in the last layer's epilogue
 torch.cuda.synchronize()
