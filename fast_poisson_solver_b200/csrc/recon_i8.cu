@@ -296,6 +296,166 @@ recon_i8_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   }
 }
 
+// ---- single-CTA form: only the digit pairs that are read back ---------------------------------------------------------
+// Orders a + b <= 4 are all the drain reads, yet the pair kernel above multiplies every W digit with the full stack of four
+// A digits (20 products, 6 of them - orders 5..7 - for nothing): under the 1 kW power cap the kernel runs at the chip's
+// sustained int8 rate, so wasted products are wasted time.  Trimming the stack per W digit (N = 256, 256, 192, 128, 64:
+// 14 products) needs the stack's PREFIX at one shared-memory address, which a cta_group::2 operand cannot offer (its N
+// halves come from the two CTAs and move with N).  Here every CTA works alone (cta_group::1, M = 128 right-hand sides)
+// and stages all four A digits itself: [d0 | d1 | d2 | d3], 32 KiB per K slab next to the five W digits (80 KiB).
+constexpr int RS_STAGE = RI_DW * RI_W_BYTES + RI_DA * RI_A_BYTES;   // 112 KiB
+constexpr int RS_SMEM = RI_STAGES * RS_STAGE + 1024 + 256;
+
+template <int N>
+__device__ __forceinline__ void umma_i8_128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(RI_THREADS, 1)
+recon_i8_solo_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const RiParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + RI_STAGES * RS_STAGE;
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 32, bar_tfull = bar_base + 64, bar_tempty = bar_base + 72;
+  const uint32_t tmem_slot = bar_base + 80;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int rhs_blocks = 2 * P.rhs_blocks;            // blocks of 128 right-hand sides
+  const int ntiles = rhs_blocks * P.point_blocks;     // tile t: rhs block t % rhs_blocks, point block t / rhs_blocks
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    for (int s = 0; s < RI_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int jb = t % rhs_blocks, ib = t / rhs_blocks;
+        const int wrow = jb * RI_TM, arow = ib * RI_TN;
+        for (int kb = 0; kb < RI_KSLABS; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * RS_STAGE;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, RS_STAGE);
+#pragma unroll
+          for (int s = 0; s < RI_DW; ++s) tma_load_2d<1>(sa + s * RI_W_BYTES, &tmW, full, kb * 128, s * P.b_pad + wrow);
+#pragma unroll
+          for (int s = 0; s < RI_DA; ++s)
+            tma_load_2d<1>(sa + RI_DW * RI_W_BYTES + s * RI_A_BYTES, &tmA, full, kb * 128, s * P.n_pad + arow);
+          if (++stage == RI_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(bar_tempty, tphase);   // accumulators read
+        tphase ^= 1;
+        tc_fence_after();
+        for (int kb = 0; kb < RI_KSLABS; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * RS_STAGE;
+          const uint64_t db = umma_desc<128>(sa + RI_DW * RI_W_BYTES);    // stack [d0 | d1 | d2 | d3], 64 rows each
+          const int ksteps = (kb == RI_KSLABS - 1) ? (FP - 128 * (RI_KSLABS - 1)) / 32 : 4;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t adv = (uint64_t)((j * 32) >> 4);
+            // W digit a times the A digits b <= 4 - a, into the window that starts at column 64 a: column group o
+            // collects a + b = o.  The first step of a tile overwrites: digit 0 initialises columns [0, 256), digit 4
+            // columns [256, 320); the windows of digits 1..3 then only touch initialised columns.
+            const uint32_t keep = (kb > 0 || j > 0) ? 1u : 0u;
+            umma_i8_128<256>(tmem_base, umma_desc<128>(sa) + adv, db + adv, keep);
+            umma_i8_128<64>(tmem_base + 4 * RI_TN, umma_desc<128>(sa + 4 * RI_W_BYTES) + adv, db + adv, keep);
+            umma_i8_128<256>(tmem_base + 1 * RI_TN, umma_desc<128>(sa + 1 * RI_W_BYTES) + adv, db + adv, 1u);
+            umma_i8_128<192>(tmem_base + 2 * RI_TN, umma_desc<128>(sa + 2 * RI_W_BYTES) + adv, db + adv, 1u);
+            umma_i8_128<128>(tmem_base + 3 * RI_TN, umma_desc<128>(sa + 3 * RI_W_BYTES) + adv, db + adv, 1u);
+          }
+          umma_commit<1>(bar_empty + 8 * stage);
+          if (++stage == RI_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<1>(bar_tfull);
+      }
+    }
+  } else {
+    // ================= drain warps 2..9 =================
+    const int quad = warp % 4;          // TMEM lanes [32 quad, 32 quad + 32) = right-hand sides
+    const int half = (warp - 2) / 4;    // 32 of the 64 points
+    const uint32_t taddr = tmem_base + half * (RI_TN / 2) + ((uint32_t)(quad * 32) << 16);
+    if (lane == 0) mbar_arrive(bar_tempty);   // the accumulators are free from the start
+    uint32_t tphase = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int jb = t % rhs_blocks, ib = t / rhs_blocks;
+      const int j = jb * RI_TM + quad * 32 + lane;
+      const bool j_ok = j < P.B;
+      const int g = j_ok ? P.gw[j] - 38 + 8 * (RI_DA + RI_DW - 2) : 0;
+      const double scale = __longlong_as_double((long long)(1023 + g - 32) << 52);
+      const double bj = (j_ok && P.bias) ? P.bias[j] : 0.0;
+      const int64_t i0 = (int64_t)ib * RI_TN + half * (RI_TN / 2);
+      mbar_wait(bar_tfull, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+      long long S[RI_TN / 2];
+#pragma unroll
+      for (int c = 0; c < RI_TN / 32; ++c) {
+        int v[RI_NORD][16];
+#pragma unroll
+        for (int o = 0; o < RI_NORD; ++o) ri_tmem_ld16(taddr + o * RI_TN + c * 16, v[o]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          long long acc = v[0][q];
+#pragma unroll
+          for (int o = 1; o < RI_NORD; ++o) acc = acc * 256 + v[o][q];
+          S[c * 16 + q] = acc;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty);
+#pragma unroll
+      for (int q = 0; q < RI_TN / 2; ++q) {
+        const int64_t i = i0 + q;
+        if (j_ok && i < P.n) P.out[i * P.ldo + j] = (float)fma((double)S[q], scale, bj);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---- host -----------------------------------------------------------------------------------------------
 struct RiState {
   int8_t* pa = nullptr;      // context-owned digit planes of A (uncached entry point): RI_DA x n_pad x FP
@@ -330,6 +490,7 @@ static int ri_state_get(fps_ctx* ctx, RiState** out) {
     FPS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &s->encode, cudaEnableDefault, &qres));
     FPS_REQUIRE(s->encode && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
     FPS_CUDA(cudaFuncSetAttribute(recon_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RI_SMEM));
+    FPS_CUDA(cudaFuncSetAttribute(recon_i8_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
   }
   *out = s;
   return 0;
@@ -414,7 +575,15 @@ static int ri_run(fps_ctx* ctx, RiState* s, const Xop* x, const int8_t* planes, 
   const int64_t ntiles = (int64_t)P.rhs_blocks * P.point_blocks;
   FPS_REQUIRE(ntiles < ((int64_t)1 << 31), "recon_i8: too many tiles");
   const int groups = (int)std::min<int64_t>(ntiles, pairs);
-  recon_i8_kernel<<<groups * 2, RI_THREADS, RI_SMEM, st>>>(tmW, tmA, P);
+  // default: the single-CTA kernel that issues only the 14 digit pairs that are read back (see above; 4 096 RHS x 262 144
+  // points, H and DH: 21.4 -> 17.0 ms); FPS_RECON_SOLO=0 selects the pair kernel with all 20 (A/B measurements)
+  static const int solo = getenv("FPS_RECON_SOLO") ? atoi(getenv("FPS_RECON_SOLO")) : 1;
+  if (solo) {
+    const int ctas = (int)std::min<int64_t>(2 * ntiles, ctx->sm_count);
+    recon_i8_solo_kernel<<<ctas, RI_THREADS, RS_SMEM, st>>>(tmW, tmA, P);
+  } else {
+    recon_i8_kernel<<<groups * 2, RI_THREADS, RI_SMEM, st>>>(tmW, tmA, P);
+  }
   FPS_CUDA(cudaGetLastError());
   count_launch(3);
   return 0;
