@@ -10,8 +10,9 @@
 //   W (704 x B fp64)            W'[k, j] = W[k, j] 2^(e_k - 30) (exact), Y[k, j] = rint(W' 2^(38 - g_j)) with g_j from the
 //                               column maximum of W': a 39-bit integer, five digits; planes pw[d][j][k]
 //   out[i, j] = 2^(g_j - 38) sum_k X[i, k] Y[k, j] + bias[j],   X Y = sum_{a, b} 2^(8 (7 - a - b)) (Wd_a . Ad_b)
-// One tcgen05.mma.kind::i8 instruction multiplies one W digit (M = 256 right-hand sides per CTA pair) with the stack
-// of all four A digits of 64 points (N = 256) into the TMEM window that starts at column 64 a, so that column group
+// One tcgen05.mma.kind::i8 instruction multiplies one W digit (pair kernel: M = 256 right-hand sides per CTA pair; solo
+// kernel, the default: M = 128 per CTA) with a stack of A digits of 64 points (pair: all four, N = 256; solo: the digits
+// b <= 4 - a that are read back) into the TMEM window that starts at column 64 a, so that column group
 // o collects the digit pairs with a + b = o (see gram_i8.cu).  K = 704 = 22 instructions of 32 per digit; the int32
 // accumulators cannot overflow (5 pairs x 704 x 2^14 < 2^26).  Orders 0..4 are combined exactly in a 64-bit integer
 // by the drain warps (orders 5..7 weigh < 2^-40 of the largest term and are not read), scaled, biased, stored as fp32.
