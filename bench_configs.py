@@ -153,8 +153,9 @@ def run_c4(env, domain="lshape", points=4194304, reps=2):
     ms_pre = env.timed(lambda: s.precompute(xd, yd, xbd, ybd), reps)
     f = perlin_sources(s, perlin_params(1, seed=5))
     bc = torch.full((bhi - blo,), 2.5, device=env.dev)
-    s.solve(f, bc)
-    ms_solve = env.timed(lambda: s.solve(f, bc), reps)
+    for _ in range(2):
+        s.solve(f, bc)
+    ms_solve = env.timed(lambda: s.solve(f, bc), max(reps, 6))     # ms-scale calls: a single host hiccup must not dominate
     u, u_pde, u_bc, f_pred, _ = s.solve(f, bc)
     # residual metrics (analyze.py:107-119), reduced over ranks
     acc = torch.stack([((f_pred - f) ** 2).sum().double(), (f ** 2).sum().double(), (f_pred - f).abs().sum().double(),
