@@ -61,7 +61,6 @@ SIGNATURES = {
     "fps_project_rhs": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "fps_solve_factored": (_i32, [_vp, _vp, _vp, _i64, _i32, _f64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "fps_reconstruct": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
-    "fps_mse": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "fps_sse_columns": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "fps_sse_columns_f64": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "fps_exact_min_rows": (_i64, []),

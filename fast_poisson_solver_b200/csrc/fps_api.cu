@@ -571,11 +571,6 @@ int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double*
   return launch_reconstruct(ctx, A, n, ld, W64, ldw, bias64, B, out, ldo, (cudaStream_t)stream);
 }
 
-int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream) {
-  FPS_REQUIRE(ctx && pred && ref && loss64 && n > 0, "fps_mse: bad argument");
-  return launch_mse(pred, ref, n, loss64, (cudaStream_t)stream);
-}
-
 int fps_sse_columns(fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr, const double* ref_const,
                     int64_t n, int B, double* sse64, void* stream) {
   FPS_REQUIRE(ctx && pred && (ref || ref_const) && sse64 && ldp >= B && (ref_const || ldr >= B), "fps_sse_columns: bad argument");

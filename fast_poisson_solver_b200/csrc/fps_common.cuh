@@ -207,7 +207,6 @@ int launch_solve_factored(const fps_ctx* ctx, const double* L, const double* R, 
                           cudaStream_t st);
 int launch_reconstruct(const fps_ctx* ctx, const float* A, int64_t n, int64_t ld, const double* W, int64_t ldw,
                        const double* bias, int B, float* out, int64_t ldo, cudaStream_t st);
-int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st);
 int launch_sse_columns(const fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr,
                        const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st);
 int launch_sse_columns_d(const fps_ctx* ctx, const double* pred, int64_t ldp, const double* ref, int64_t ldr,

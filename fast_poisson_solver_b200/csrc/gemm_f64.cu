@@ -647,27 +647,6 @@ int launch_reconstruct_d(const fps_ctx* ctx, const double* A, int64_t n, int64_t
   return launch_reconstruct_t<double, double>(ctx, A, n, ld, W, ldw, bias, B, out, ldo, st);
 }
 
-// mean((pred - ref)^2) in fp64, single CTA (used only by the multi-lambda sweep, solver.py:312-314).
-__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ ref, int64_t n,
-                           double* __restrict__ loss) {
-  __shared__ double red[32];
-  double s = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double d = (double)pred[i] - (double)ref[i];
-    s = fma(d, d, s);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    s = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) loss[0] = s / (double)n;
-  }
-}
-
 // Batched form (multi-lambda sweep over B right-hand sides): sse[j] += sum_i (pred[i][j] - ref[i][j])^2.
 // CTA = 32 columns x 8 row lanes over one row chunk; partial sums per chunk go to the split-K workspace and are summed in
 // chunk order (bit-reproducible).  ref_const: one reference value per column instead of a matrix.
@@ -728,13 +707,6 @@ int launch_sse_columns(const fps_ctx* ctx, const float* pred, int64_t ldp, const
 int launch_sse_columns_d(const fps_ctx* ctx, const double* pred, int64_t ldp, const double* ref, int64_t ldr,
                          const double* ref_const, int64_t n, int B, double* sse, cudaStream_t st) {
   return launch_sse_columns_t<double>(ctx, pred, ldp, ref, ldr, ref_const, n, B, sse, st);
-}
-
-int launch_mse(const float* pred, const float* ref, int64_t n, double* loss, cudaStream_t st) {
-  mse_kernel<<<1, 1024, 0, st>>>(pred, ref, n, loss);
-  count_launch();
-  FPS_CUDA(cudaGetLastError());
-  return 0;
 }
 
 }  // namespace fps

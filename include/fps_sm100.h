@@ -165,9 +165,7 @@ int fps_solve_factored(fps_ctx* ctx, const double* L64, const double* R64, int64
 int fps_reconstruct(fps_ctx* ctx, float* A, int64_t n, int64_t ld, const double* W64, int64_t ldw,
                     const double* bias64, int B, float* out, int64_t ldo, void* stream);
 
-/* Multi-lambda loss of solver.py:312-314 for one lambda: loss64[0] = mean((pred-ref)^2).        */
-int fps_mse(fps_ctx* ctx, const float* pred, const float* ref, int64_t n, double* loss64, void* stream);
-/* The same for B right-hand sides at once (the batched multi-lambda sweep): sse64[j] += sum_i (pred[i][j] - ref[i][j])^2,
+/* Multi-lambda losses of solver.py:312-314 for B right-hand sides at once: sse64[j] += sum_i (pred[i][j] - ref[i][j])^2,
  * j < B; pred (n, ldp), ref (n, ldr) float32.  ref_const != NULL: ref[i][j] = ref_const[j] (float64; constant boundary
  * values) and ref / ldr are ignored.  Accumulating (zero sse64 first); fixed summation order.                          */
 int fps_sse_columns(fps_ctx* ctx, const float* pred, int64_t ldp, const float* ref, int64_t ldr,
