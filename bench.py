@@ -476,7 +476,14 @@ def run_ours(args):
 
         del solver
         torch.cuda.empty_cache()
-        strong = strong_block(Env(), quick=args.quick)
+        try:
+            strong = strong_block(Env(), quick=args.quick)
+        except Exception as e:      # the headline line must survive a failure of the extra configurations
+            import traceback
+
+            traceback.print_exc()
+            strong = {"scaling": "strong", "n_gpus": world, "error": f"{type(e).__name__}: {e}"[:500]}
+            torch.cuda.empty_cache()
 
     if world > 1:
         dist.barrier()
